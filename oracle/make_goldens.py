@@ -1,0 +1,219 @@
+"""Pin the oracle against the REAL reference and write tests/golden/*.npz.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Run in the build container, where /root/reference
+exists:   python -m oracle.make_goldens
+For every case the real reference (imported by oracle/ref_bootstrap.py, unmodified) is executed on
+the synthetic weights of oracle/weights.py; the restatement in oracle/{llada,denoise,magvit}.py
+is asserted bit-identical to it; and the REFERENCE's outputs are stored as the golden vectors.
+The fixtures are small (ids, masks, sub-sampled logits, checksums); big inputs (weights, noise)
+are regenerated deterministically from seeds at test time.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import denoise, llada, magvit, ref_bootstrap as rb, weights as W
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _save(name, **arrs):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrs.items()})
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def t2i_case(name, cfg, B, P, N, steps, guidance, wseed, pseed, gseed):
+    print(f"[t2i] {name}")
+    sd = W.make_llada_weights(cfg, wseed)
+    model = rb.build_model(cfg, sd)
+    cond, unc, am, uam = W.make_t2i_prompts(B, P, N, pseed)
+    # --- the real reference
+    ids_ref = cond.clone()
+    g = torch.Generator().manual_seed(gseed)
+    t0 = time.time()
+    out_ref = model.t2i_generate(input_ids=ids_ref, uncond_input_ids=unc.clone(), attention_mask=am,
+                                 uncond_attention_mask=uam, guidance_scale=guidance, timesteps=steps,
+                                 seq_len=N, resolution=P - 1, generator=g,
+                                 uni_prompting=rb.UniPromptingStub(W.TEXT_VOCAB))
+    print(f"  reference t2i_generate: {time.time() - t0:.1f}s")
+    # --- the restatement, full-vocab logits, same generator seed
+    ids_or = cond.clone()
+    trace = []
+    out_or = denoise.t2i_generate(lambda x: llada.forward_logits(x, sd, cfg), ids_or, unc.clone(),
+                                  guidance_scale=guidance, timesteps=steps, seq_len=N, resolution=P - 1,
+                                  generator=torch.Generator().manual_seed(gseed), trace=trace)
+    assert torch.equal(out_ref, out_or), "restatement != reference (sampled_ids)"
+    assert torch.equal(ids_ref, ids_or), "restatement != reference (mutated input_ids)"
+    # --- restricted lm_head (image rows x codebook columns) must give the same decisions
+    ids_sl = cond.clone()
+    rows, cols = slice(-(N + 1), -1), slice(W.TEXT_VOCAB, W.TEXT_VOCAB + W.CODEBOOK)
+    out_sl = denoise.t2i_generate(lambda x: llada.forward_logits(x, sd, cfg, rows, cols), ids_sl, unc.clone(),
+                                  guidance_scale=guidance, timesteps=steps, seq_len=N, resolution=P - 1,
+                                  generator=torch.Generator().manual_seed(gseed), sliced_logits=True)
+    same = torch.equal(out_sl, out_ref) and torch.equal(ids_sl, ids_ref)
+    print(f"  restricted lm_head reproduces reference ids: {same}")
+    # the reference's own first-forward logits (for the tolerance-based logits parity test)
+    with torch.no_grad():
+        lg = model(torch.cat([cond, unc])).logits[:, rows, cols]
+    _save(name,
+          sampled_ids=out_ref, final_input_ids=ids_ref, cond_ids=cond, uncond_ids=unc,
+          step_sampled=torch.stack([t["sampled_ids"] for t in trace]),
+          step_masking=torch.stack([t["masking"] for t in trace]),
+          step_mask_len=torch.stack([t["mask_len"] for t in trace]),
+          step_sel=torch.stack([t["selected_probs"] for t in trace]),
+          step_u=torch.stack([t["u"] for t in trace]),
+          step_q_sum=np.array([float(t["q"].double().sum()) for t in trace]),
+          step_temperature=np.array([t["temperature"] for t in trace]),
+          step_mask_len_raw=np.array([t["mask_len_raw"] for t in trace]),
+          step_cond_sub=torch.stack([t["cond"][:, ::16, ::64] for t in trace]),
+          step_uncond_sub=torch.stack([t["uncond"][:, ::16, ::64] for t in trace]),
+          first_logits_sub=lg[:, ::4, ::32], first_logits_absmax=lg.abs().max(), first_logits_std=lg.std(),
+          restricted_same=np.array(same),
+          meta=np.array([B, P, N, steps, wseed, pseed, gseed]), guidance=np.array(guidance))
+
+
+def text_case(name, cfg, B, Lp, gen, block, steps, temperature, cfg_scale, wseed, seed, fast_eot=None):
+    print(f"[text] {name}")
+    sd = W.make_llada_weights(cfg, wseed)
+    model = rb.build_model(cfg, sd)
+    g = torch.Generator().manual_seed(seed)
+    prompt = torch.randint(0, 126000, (B, Lp), generator=g)
+    gen_fn = rb.load_generate_fn()
+    torch.manual_seed(seed)
+    x_ref = gen_fn(model, prompt, steps=steps, gen_length=gen, block_length=block, temperature=temperature,
+                   cfg_scale=cfg_scale, remasking="low_confidence")
+    torch.manual_seed(seed)
+    x_mmu = model.mmu_generate(idx=prompt, max_new_tokens=gen, steps=steps, block_length=block,
+                               temperature=temperature, cfg_scale=cfg_scale)
+    assert torch.equal(x_ref, x_mmu), "generate() != mmu_generate()"
+    torch.manual_seed(seed)
+    trace = []
+    x_or = denoise.generate(lambda x: llada.forward_logits(x, sd, cfg), prompt, steps=steps, gen_length=gen,
+                            block_length=block, temperature=temperature, cfg_scale=cfg_scale, trace=trace)
+    assert torch.equal(x_ref, x_or), "restatement != reference (generate)"
+    extra = {}
+    if fast_eot is not None:
+        eot = int(x_ref[0, Lp + block - 1]) if fast_eot == "hit" else 5
+        torch.manual_seed(seed)
+        x_fast = model.mmu_generate_fast(idx=prompt[:1], max_new_tokens=gen, steps=steps, block_length=block,
+                                         temperature=temperature, cfg_scale=cfg_scale, eot_token=eot)
+        torch.manual_seed(seed)
+        x_fo = denoise.generate(lambda x: llada.forward_logits(x, sd, cfg), prompt[:1], steps=steps,
+                                gen_length=gen, block_length=block, temperature=temperature,
+                                cfg_scale=cfg_scale, eot_token=eot)
+        assert torch.equal(x_fast, x_fo), "restatement != reference (mmu_generate_fast)"
+        extra = dict(fast_x=x_fast, fast_eot=np.array(eot))
+    _save(name, x=x_ref, prompt=prompt,
+          step_x=torch.stack([t["x"] for t in trace]),
+          step_transfer=torch.stack([t["transfer"] for t in trace]),
+          meta=np.array([B, Lp, gen, block, steps, wseed, seed]),
+          temperature=np.array(temperature), cfg_scale=np.array(cfg_scale), **extra)
+
+
+def sampling_case():
+    print("[sampling]")
+    _, _, sp, _ = rb.modules()
+    tabs = {}
+    for N in (64, 256, 1024):
+        for T in (8, 15, 18):
+            ref = [float((N * sp.cosine_schedule(torch.tensor(1.0 * (s + 1) / T))).floor()) for s in range(T)]
+            assert ref == denoise.t2i_mask_len_schedule(N, T)
+            tabs[f"cos_{N}_{T}"] = np.array(ref)
+    assert list(tabs["cos_1024_15"][[9, 14]]) == [511.0, -1.0]
+    g = torch.Generator().manual_seed(7)
+    probs = torch.rand(4, 256, generator=g) ** 4
+    probs[:, ::5] = torch.finfo(torch.float32).max
+    probs[1, 10:40] = probs[1, 10]                      # ties at/around the cut-off
+    mask_len = torch.tensor([[1.0], [20.0], [100.0], [200.0]])
+    outs = []
+    for T in (0.0, 0.3, 1.0):
+        gr = torch.Generator().manual_seed(11)
+        ref = sp.mask_by_random_topk(mask_len, probs, T, generator=gr)
+        go = torch.Generator().manual_seed(11)
+        assert torch.equal(ref, denoise.mask_by_random_topk(mask_len, probs, T, generator=go))
+        outs.append(ref)
+    u = torch.zeros_like(probs).uniform_(0, 1, generator=torch.Generator().manual_seed(11))
+    for name in ("linear", "pow2", "sigmoid"):
+        f = sp.get_mask_schedule(name)
+        tabs["sched_" + name] = np.array([float(f(torch.tensor(t))) for t in np.linspace(0, 1, 11)])
+    _save("sampling", probs=probs, mask_len=mask_len, u=u, masking=torch.stack(outs),
+          temperatures=np.array([0.0, 0.3, 1.0]), **tabs)
+
+
+def magvit_case():
+    print("[magvit]")
+    sd = W.make_vq_decoder_weights(0)
+    vq = rb.build_vq(sd)
+    # LFQ tables against the reference's buffers
+    all_idx = torch.arange(8192).view(8, 1024)
+    ref_bits = vq.quantize.get_codebook_entry(all_idx)
+    assert np.array_equal(ref_bits.numpy(), magvit.lfq_indices_to_bits(all_idx.numpy()))
+    ref_idx = vq.quantize.get_indices(ref_bits)
+    assert np.array_equal(ref_idx.numpy(), magvit.lfq_bits_to_indices(ref_bits.numpy()))
+    assert torch.equal(ref_idx.reshape(8, 1024), all_idx)
+    g = torch.Generator().manual_seed(3)
+    out = {}
+    for tag, B, n in (("8x8", 2, 64), ("16x16", 1, 256)):
+        idx = torch.randint(0, 8192, (B, n), generator=g)
+        with torch.no_grad():
+            ref = vq.decode_code(idx)
+        taps = {}
+        mine = magvit.decode_code(idx, sd, taps)
+        assert torch.equal(ref, mine), "restatement != reference (decode_code)"
+        out[f"idx_{tag}"] = idx
+        out[f"pix_{tag}"] = ref if n == 64 else ref[:, :, ::2, ::2]
+        out[f"pix_absmax_{tag}"] = ref.abs().max()
+        out[f"tap_names_{tag}"] = np.array(list(taps.keys()))
+        out[f"tap_mean_{tag}"] = np.array([float(v.double().mean()) for v in taps.values()])
+        out[f"tap_std_{tag}"] = np.array([float(v.double().std()) for v in taps.values()])
+    _save("magvit", bits_sample_idx=torch.tensor([0, 5, 4096, 8191]),
+          bits_sample=vq.quantize.get_codebook_entry(torch.tensor([[0, 5, 4096, 8191]])), **out)
+
+
+def logits_case(name, cfg, B, L, wseed, seed):
+    print(f"[logits] {name}")
+    sd = W.make_llada_weights(cfg, wseed)
+    model = rb.build_model(cfg, sd)
+    ids = torch.randint(0, 126000, (B, L), generator=torch.Generator().manual_seed(seed))
+    ids[:, L // 2:] = cfg["mask_token_id"]
+    with torch.no_grad():
+        ref = model(ids).logits
+        # Q1: the bias is never applied
+        bias = torch.zeros(B, 1, L, L, dtype=torch.bool)
+        assert torch.equal(ref, model(ids, attention_bias=bias).logits)
+    mine = llada.forward_logits(ids, sd, cfg)
+    assert torch.equal(ref, mine), "restatement != reference (logits)"
+    cols = slice(W.TEXT_VOCAB, W.TEXT_VOCAB + W.CODEBOOK)
+    _save(name, ids=ids, logits_img=ref[:, ::3, cols][:, :, ::16], logits_txt=ref[:, ::3, :126000:512],
+          absmax=ref.abs().max(), std=ref.std(), meta=np.array([B, L, wseed, seed]))
+
+
+def main():
+    assert rb.available(), "needs /root/reference (build container)"
+    torch.set_num_threads(os.cpu_count())
+    sampling_case()
+    magvit_case()
+    logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
+    logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
+    t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)
+    t2i_case("t2i_tiny128", W.TINY128, B=2, P=17, N=256, steps=8, guidance=2.0, wseed=1, pseed=2, gseed=99)
+    text_case("text_t0", W.TINY, B=3, Lp=12, gen=32, block=8, steps=16, temperature=0.0, cfg_scale=0.0,
+              wseed=0, seed=21, fast_eot="hit")
+    text_case("text_t1", W.TINY, B=3, Lp=12, gen=32, block=8, steps=16, temperature=1.0, cfg_scale=0.0,
+              wseed=0, seed=22, fast_eot="miss")
+    text_case("text_cfg", W.TINY, B=2, Lp=10, gen=32, block=16, steps=8, temperature=0.7, cfg_scale=1.5,
+              wseed=0, seed=23)
+    if "--skip-c1" not in sys.argv:
+        t2i_case("t2i_c1", W.C1, B=1, P=129, N=256, steps=15, guidance=3.5, wseed=0, pseed=0, gseed=1234)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+"""Synthetic model configurations and weights shared by the oracle, the goldens and the tests.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  There is no network, hence no
+checkpoint: every parity case runs on random weights.  The generator below is
+deliberately independent of the reference's own ``init_weights``
+(/root/reference/models/modeling_llada.py:80-155) so that it can be re-run on the
+GPU box, where the reference is absent, and give bit-identical tensors: each
+tensor gets its own ``torch.Generator`` seeded from (seed, key name).  The scale
+follows the reference's "mitchell" rule (std = 1/sqrt(fan_in), residual outputs
+further divided by sqrt(2*(layer+1)), truncation at 3 std) so logits have a
+realistic O(1) scale.
+
+Key names are the reference's state-dict names so the same
+dict loads into the real ``MMadaModelLM`` / ``MAGVITv2`` with ``load_state_dict``.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from typing import Dict
+
+import torch
+
+# --- configurations -----------------------------------------------------------------------
+
+#: BASELINE.json configs[0]: reduced LLaDA/MMaDA, 4 layers, d=1024 (heads / ffn pinned here).
+C1 = dict(d_model=1024, n_heads=16, n_layers=4, mlp_hidden_size=2816, vocab_size=134656,
+          rope_theta=500000.0, rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
+
+#: BASELINE.json configs[1]: MMaDA-8B architecture (configs/mmada_demo.yaml + LLaDA-8B config).
+C2 = dict(d_model=4096, n_heads=32, n_layers=32, mlp_hidden_size=12288, vocab_size=134656,
+          rope_theta=500000.0, rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
+
+#: tiny model for fast unit tests (head_dim 64) and its head_dim-128 sibling
+TINY = dict(d_model=256, n_heads=4, n_layers=2, mlp_hidden_size=512, vocab_size=134656,
+            rope_theta=500000.0, rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
+TINY128 = dict(TINY, d_model=512, n_heads=4, mlp_hidden_size=1024)
+
+#: `len(uni_prompting.text_tokenizer)` stand-in (reference app.py:396); image code c has id c + this.
+TEXT_VOCAB = 126349
+CODEBOOK = 8192
+# reserved token ids (reference training/prompting_utils.py:17-33)
+TOK_SOI, TOK_EOI, TOK_T2I, TOK_MMU, TOK_PAD = 126084, 126085, 126088, 126089, 126093
+TOK_BOS, TOK_EOS = 126080, 126081
+
+
+def _gen(seed: int, name: str) -> torch.Generator:
+    h = hashlib.sha256(f"{seed}:{name}".encode()).digest()
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int.from_bytes(h[:7], "little"))
+    return g
+
+
+def _normal(seed: int, name: str, shape, std: float, dtype=torch.float32) -> torch.Tensor:
+    t = torch.randn(shape, generator=_gen(seed, name), dtype=torch.float32)
+    t.clamp_(-3.0, 3.0).mul_(std)
+    return t.to(dtype)
+
+
+def make_llada_weights(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """State dict with the reference's key names for ``cfg`` (no biases, untied head)."""
+    d, ffn, V = cfg["d_model"], cfg["mlp_hidden_size"], cfg["vocab_size"]
+    sd: Dict[str, torch.Tensor] = {}
+    p = "model.transformer."
+    sd[p + "wte.weight"] = _normal(seed, "wte", (V, d), 1.0 / math.sqrt(d), dtype)
+    for i in range(cfg["n_layers"]):
+        b = f"{p}blocks.{i}."
+        res = 1.0 / math.sqrt(2 * (i + 1))
+        sd[b + "attn_norm.weight"] = (1.0 + _normal(seed, b + "attn_norm", (d,), 0.1)).to(dtype)
+        sd[b + "ff_norm.weight"] = (1.0 + _normal(seed, b + "ff_norm", (d,), 0.1)).to(dtype)
+        for n in ("q_proj", "k_proj", "v_proj"):
+            sd[b + n + ".weight"] = _normal(seed, b + n, (d, d), 1.0 / math.sqrt(d), dtype)
+        sd[b + "attn_out.weight"] = _normal(seed, b + "attn_out", (d, d), res / math.sqrt(d), dtype)
+        sd[b + "ff_proj.weight"] = _normal(seed, b + "ff_proj", (ffn, d), 1.0 / math.sqrt(d), dtype)
+        sd[b + "up_proj.weight"] = _normal(seed, b + "up_proj", (ffn, d), 1.0 / math.sqrt(d), dtype)
+        sd[b + "ff_out.weight"] = _normal(seed, b + "ff_out", (d, ffn), res / math.sqrt(ffn), dtype)
+    sd[p + "ln_f.weight"] = (1.0 + _normal(seed, "ln_f", (d,), 0.1)).to(dtype)
+    sd[p + "ff_out.weight"] = _normal(seed, "head", (V, d), 1.0 / math.sqrt(d), dtype)
+    return sd
+
+
+def make_t2i_prompts(batch: int, prefix_len: int, n_img: int, seed: int = 0, mask_id: int = 126336):
+    """Synthetic t2i_gen rows laid out like reference training/prompting_utils.py:200-233:
+    ``[pad.. <|t2i|> bos text eos]`` (prefix_len ids, left padded) ``<|soi|> mask*n_img <|eoi|>``.
+    Returns (cond_ids, uncond_ids, cond_attn, uncond_attn), all int64 (batch, prefix_len+n_img+2)."""
+    g = _gen(seed, "prompts")
+    L = prefix_len + 1 + n_img + 1
+    cond = torch.full((batch, L), TOK_PAD, dtype=torch.int64)
+    unc = torch.full((batch, L), TOK_PAD, dtype=torch.int64)
+    for b in range(batch):
+        t = int(torch.randint(4, min(64, prefix_len - 3) + 1, (1,), generator=g))
+        text = torch.randint(0, 126000, (t,), generator=g)
+        row = torch.cat([torch.tensor([TOK_T2I, TOK_BOS]), text, torch.tensor([TOK_EOS])])
+        cond[b, prefix_len - row.numel():prefix_len] = row
+        urow = torch.tensor([TOK_T2I, TOK_BOS, TOK_EOS])
+        unc[b, prefix_len - 3:prefix_len] = urow
+    for ids in (cond, unc):
+        ids[:, prefix_len] = TOK_SOI
+        ids[:, prefix_len + 1:prefix_len + 1 + n_img] = mask_id
+        ids[:, -1] = TOK_EOI
+    return cond, unc, (cond != TOK_PAD).long(), (unc != TOK_PAD).long()
+
+
+# --- MAGVIT-v2 decoder --------------------------------------------------------------------
+
+VQ_CH, VQ_CH_MULT, VQ_NUM_RES, VQ_Z = 128, (1, 1, 2, 2, 4), (4, 4, 3, 4, 3), 13
+
+
+def vq_decoder_plan():
+    """Decoder topology as a flat list of (kind, key-prefix, c_in, c_out), following
+    reference models/modeling_magvitv2.py:309-362 / :365-399 (up levels iterated 4..0)."""
+    plan = [("conv1", "post_quant_conv", VQ_Z, VQ_Z)]
+    c = VQ_CH * VQ_CH_MULT[-1]
+    plan += [("conv3", "conv_in", VQ_Z, c), ("res", "mid.block_1", c, c), ("attn", "mid.attn_1", c, c),
+             ("res", "mid.block_2", c, c)]
+    for lvl in reversed(range(5)):
+        co = VQ_CH * VQ_CH_MULT[lvl]
+        for j in range(VQ_NUM_RES[lvl]):
+            plan.append(("res", f"up.{lvl}.block.{j}", c, co))
+            c = co
+        if lvl != 0:
+            plan.append(("up", f"up.{lvl}.upsample", c, c))
+    plan += [("norm_out", "norm_out", c, c), ("conv3", "conv_out", c, 3)]
+    return plan
+
+
+def make_vq_decoder_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for ``MAGVITv2.decoder`` with the reference's key names, prefixed 'decoder.'."""
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        std = 1.0 / math.sqrt(ci * k * k)
+        sd[f"decoder.{name}.weight"] = _normal(seed, name + ".w", (co, ci, k, k), std)
+        sd[f"decoder.{name}.bias"] = _normal(seed, name + ".b", (co,), 0.02)
+
+    def norm(name, c):
+        sd[f"decoder.{name}.weight"] = 1.0 + _normal(seed, name + ".w", (c,), 0.1)
+        sd[f"decoder.{name}.bias"] = _normal(seed, name + ".b", (c,), 0.05)
+
+    for kind, key, ci, co in vq_decoder_plan():
+        if kind == "conv1":
+            conv(key, co, ci, 1)
+        elif kind == "conv3":
+            conv(key, co, ci, 3)
+        elif kind == "res":
+            norm(key + ".norm1", ci); conv(key + ".conv1", co, ci, 3)
+            norm(key + ".norm2", co); conv(key + ".conv2", co, co, 3)
+            if ci != co:
+                conv(key + ".nin_shortcut", co, ci, 1)
+        elif kind == "attn":
+            norm(key + ".norm", ci)
+            for n in ("q", "k", "v", "proj_out"):
+                conv(f"{key}.{n}", co, ci, 1)
+        elif kind == "up":
+            conv(key + ".conv", co, ci, 3)
+        elif kind == "norm_out":
+            norm(key, ci)
+    return sd
