@@ -1,0 +1,91 @@
+/*
+ * mmada_b200 — C ABI of the B200 (sm_100a) kernels behind MMaDA's masked-diffusion denoising path.
+ *
+ * The reference (MercuryCod/MMaDA) is pure Python/PyTorch and has no FFI: its "operators" for this
+ * path are PyTorch library calls.  Each entry point below replaces one of those call sites (cited as
+ * file:line under /root/reference) and is what a maintainer would bind with ctypes/cffi from the
+ * reference's Python.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - the library never allocates or frees caller-visible memory and keeps no global state beyond
+ *     lazily queried device attributes;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and returns immediately: 0 on success, 1..99 argument/shape errors, 1000+cudaError_t for
+ *     CUDA runtime errors.  No exceptions cross the ABI.
+ *   - bf16 = 16-bit bfloat16 storage, row-major, leading dimensions in ELEMENTS.
+ */
+#ifndef MMADA_B200_H
+#define MMADA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMADA_ABI_VERSION 1
+int mmada_abi_version(void);
+/* Compute capability of the current device as major*10+minor (100 for B200); <0 on error. */
+int mmada_device_arch(void);
+
+/* ---- dense projections -------------------------------------------------------------------
+ * out = epilogue(A[M,K] . B[N,K]^T), A and B bf16 (K contiguous), fp32 accumulate (tcgen05/TMEM).
+ * Replaces nn.Linear at models/modeling_llada.py:901-903 (q/k/v_proj), :724 (attn_out),
+ * :924 (ff_proj, up_proj), :930 (ff_out), :1362 (transformer.ff_out == lm_head).            */
+enum {
+    MMADA_EPI_BF16 = 0,        /* out bf16 [M,N]                                                     */
+    MMADA_EPI_F32 = 1,         /* out fp32 [M,N]                                                     */
+    MMADA_EPI_RESID_F32 = 2,   /* out fp32 [M,N] = aux fp32 [M,N] (same ld as out; may alias) + acc    */
+    MMADA_EPI_SWIGLU_BF16 = 3, /* out bf16 [M,N/2] = silu(gate)*up; B rows interleaved per 128:
+                                  rows [256j,256j+128) = ff_proj rows [128j,..), next 128 = up_proj  */
+    MMADA_EPI_BIAS_BF16 = 4    /* out bf16 [M,N] = acc + aux fp32 [N]                                */
+};
+int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                    const void* aux, int M, int N, int K, int epilogue, int cta_group, void* stream);
+
+/* ---- HBM-bound block kernels ----------------------------------------------------------------
+ * embed:   out fp32 [M,d] = table bf16 [vocab,d][ids[m]]         models/modeling_llada.py:1222
+ * rmsnorm: out bf16 [M_out,d] = x*rsqrt(mean(x^2)+eps)*weight     models/modeling_llada.py:315-329
+ *          x fp32 [*,d] (the fp32 residual stream); rows (int32[M_out], may be NULL) gathers input rows
+ * rope:    NeoX half-split rotary embedding in place on the q and k thirds of qkv bf16 [M,ld]
+ *          (q at column 0, k at column d_model); row m has position m % seq_len; sin/cos are the
+ *          reference's fp32 tables [>=seq_len, head_dim/2]         models/modeling_llada.py:376-428 */
+int mmada_embed_f32(const int64_t* ids, const void* table_bf16, float* out, int M, int d, int64_t vocab,
+                    void* stream);
+int mmada_rmsnorm_bf16(const float* x, const float* weight, void* out_bf16, const int32_t* rows, int M_out,
+                       int d, float eps, void* stream);
+int mmada_rope_inplace_bf16(void* qkv_bf16, int64_t ld, const float* sin_table, const float* cos_table, int M,
+                            int d_model, int head_dim, int seq_len, void* stream);
+
+/* ---- attention -----------------------------------------------------------------------------
+ * out[b*L+t, h*hd:(h+1)*hd] = softmax(q k^T * scale) v for every (b,h); bidirectional, no mask, no
+ * KV cache.  q/k/v bf16 [B*L, ld] with head h at columns h*hd (they may be the three thirds of one
+ * fused buffer); out bf16 [B*L, ldo].  head_dim 64 or 128.
+ * Replaces F.scaled_dot_product_attention at models/modeling_llada.py:653-660.              */
+int mmada_attention_bf16(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
+                         int B, int L, int H, int head_dim, float scale, void* stream);
+
+/* ---- t2i sampling step ------------------------------------------------------------------------
+ * One launch = models/modeling_mmada.py:164-209 + models/sampling.py:31-36 for one denoising step
+ * on already-sliced logits: CFG mix (uncond may be NULL), softmax, argmax(p/q), known-token
+ * override, selected probability, mask_len clamp, log p + T*gumbel(u), k-th smallest cut-off with
+ * strict '<', write-back.
+ *   cond/uncond/q fp32 [B*N, C] (C in {512,1024,2048,4096,8192}); u fp32 [B,N];
+ *   known_ids int64 [B,N] in/out (code id, or mask_id where unknown);
+ *   input_ids int64 [B, ld_ids] in/out, image tokens at columns [img_off, img_off+N) (may be NULL);
+ *   sampled_out int64 [B,N]; sel_out fp32 [B,N]; masking_out uint8 [B,N] (may be NULL);
+ *   tickets int32 [B], zero on entry and left zero.                                            */
+int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, const float* q_noise,
+                          const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
+                          int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
+                          int32_t* tickets, int B, int N, int C, float one_plus_g, float g,
+                          float mask_len_raw, float temperature, int64_t mask_id, int64_t text_vocab,
+                          void* stream);
+/* masking[b,n] = conf[b,n] < sort(conf[b])[mask_len[b]], conf = log(max(p,1e-20)) + T*gumbel(u).
+ * Replaces mask_by_random_topk, models/sampling.py:31-36.                                      */
+int mmada_mask_by_random_topk(const float* probs, const float* u_noise, const int64_t* mask_len,
+                              uint8_t* masking_out, int B, int N, float temperature, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMADA_B200_H */

@@ -1,0 +1,71 @@
+"""ctypes binding of libmmada_b200.so (the C ABI declared in include/mmada_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.  Build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C mmada_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmada_b200.so")
+
+_lib: Optional[C.CDLL] = None
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+#: name -> argtypes (restype is always int); mirrors include/mmada_b200.h
+SIGNATURES = {
+    "mmada_abi_version": [],
+    "mmada_device_arch": [],
+    "mmada_gemm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _p],
+    "mmada_embed_f32": [_p, _p, _p, _i, _i, _i64, _p],
+    "mmada_rmsnorm_bf16": [_p, _p, _p, _p, _i, _i, _f, _p],
+    "mmada_rope_inplace_bf16": [_p, _i64, _p, _p, _i, _i, _i, _i, _p],
+    "mmada_attention_bf16": [_p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _f, _p],
+    "mmada_t2i_sample_step": [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f,
+                              _i64, _i64, _p],
+    "mmada_mask_by_random_topk": [_p, _p, _p, _p, _i, _i, _f, _p],
+}
+
+
+class MMadaKernelError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise MMadaKernelError(
+                f"{LIB_PATH} not found: the CUDA extension is not built (run __graft_entry__.build()). "
+                "mmada_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            if not hasattr(lib, name):
+                continue            # reported by check_symbols(); calling it raises below
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    fn = getattr(lib, name, None)
+    if fn is None:
+        raise MMadaKernelError(f"{name} is not exported by {LIB_PATH}")
+    st = fn(*args)
+    if st != 0:
+        detail = ""
+        if st >= 1000:
+            try:
+                import torch
+                detail = f" (cudaError {st - 1000})"
+                torch.cuda.synchronize()
+            except Exception as e:  # surface the asynchronous error text if there is one
+                detail += f": {e}"
+        raise MMadaKernelError(f"{name} failed with status {st}{detail}")

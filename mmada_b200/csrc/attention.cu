@@ -1,0 +1,332 @@
+// Bidirectional (non-causal, unmasked, no KV cache) flash attention on tcgen05 / TMEM.
+//
+// Replaces F.scaled_dot_product_attention(q, k, v, attn_mask=None, is_causal=False) at
+// /root/reference/models/modeling_llada.py:653-660 (called from :711-718; the attention_bias the
+// reference builds is never applied — SURVEY.md Appendix A, Q1).
+//
+// q, k, v are read in place from the fused projection output [B*L, ld] (head h at columns h*hd),
+// the output is written token-major [B*L, ldo] ready for the attn_out GEMM: no transposes.
+//
+// One CTA handles one (batch, head) and up to two 128-row query tiles ("ping-pong"):
+//   warps 0-3 / 4-7  softmax for query tile 0 / 1, one thread per query row: tcgen05.ld the 128
+//                    scores of the row, online softmax in base 2 with lazy rescaling of the output
+//                    accumulator (only when the running max grows by more than 2^8), write P (bf16)
+//                    back into the TMEM columns the scores came from
+//   warp 8           TMA producer: Q once, then K/V tiles of 128 keys through 2-stage rings
+//   warp 9           MMA issuer: S_i = Q_i K^T (both operands K-major in shared memory) and
+//                    O_i += P_i V (P from TMEM, V as an MN-major shared-memory operand)
+// TMEM: S0 | S1 | O0 | O1  (128 + 128 + hd + hd columns).  While one tile's softmax runs, the tensor
+// pipe works on the other tile.  The last key tile is shortened to a multiple of 16 keys.
+#include <math.h>
+
+#include "common.cuh"
+#include "host_utils.h"
+#include "../../include/mmada_b200.h"
+
+namespace mmada {
+
+constexpr int ATT_THREADS = 320;
+constexpr int QT = 128;    // query rows per tile
+constexpr int KT = 128;    // keys per tile
+
+struct AttnParams {
+    __nv_bfloat16* out;
+    int64_t ldo;
+    int L, H, B;
+    float scale_log2;      // softmax scale * log2(e)
+};
+
+template <int HD>
+struct AttnCfg {
+    static constexpr int TILE_BYTES = QT * HD * 2;          // one Q / K / V tile
+    static constexpr int BOX_BYTES = QT * 64 * 2;           // one 64-column TMA box (16 KiB)
+    static constexpr int NBOX = HD / 64;
+    static constexpr int Q_OFF = 0;                         // 2 query tiles
+    static constexpr int K_OFF = 2 * TILE_BYTES;            // 2 stages
+    static constexpr int V_OFF = 4 * TILE_BYTES;            // 2 stages
+    static constexpr int BAR_OFF = 6 * TILE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int TM_S = 0;                          // S_i at TM_S + 128 i
+    static constexpr int TM_O = 256;                        // O_i at TM_O + HD i
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
+    using Cfg = AttnCfg<HD>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + Cfg::BAR_OFF;
+    // barriers: q_full | k_full[2] | k_empty[2] | v_full[2] | v_empty[2] | s_full[2] | p_full[2] | o_full[2] | tmem ptr
+    const uint32_t q_full = bars;
+    auto k_full = [&](int s) { return bars + 8 * (1 + s); };
+    auto k_empty = [&](int s) { return bars + 8 * (3 + s); };
+    auto v_full = [&](int s) { return bars + 8 * (5 + s); };
+    auto v_empty = [&](int s) { return bars + 8 * (7 + s); };
+    auto s_full = [&](int i) { return bars + 8 * (9 + i); };
+    auto p_full = [&](int i) { return bars + 8 * (11 + i); };
+    auto o_full = [&](int i) { return bars + 8 * (13 + i); };
+    const uint32_t tmem_ptr_addr = bars + 8 * 15;
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_pairs = (p.L + 2 * QT - 1) / (2 * QT);
+    const int qp = blockIdx.x % q_pairs;
+    const int bh = blockIdx.x / q_pairs;
+    const int h = bh % p.H, b = bh / p.H;
+    const int q0 = qp * 2 * QT;
+    const int n_qt = (q0 + QT < p.L) ? 2 : 1;               // second query tile entirely out of range?
+    const int n_kv = (p.L + KT - 1) / KT;
+    const int tail = p.L - (n_kv - 1) * KT;                 // valid keys in the last tile (1..128)
+    const int tail16 = (tail + 15) & ~15;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_k);
+        tma_prefetch_desc(&map_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(k_full(s), 1);
+            mbar_init(k_empty(s), 1);
+            mbar_init(v_full(s), 1);
+            mbar_init(v_empty(s), 1);
+            mbar_init(s_full(s), 1);
+            mbar_init(p_full(s), 128);
+            mbar_init(o_full(s), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc<1>(tmem_ptr_addr, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+
+    if (warp == 8) {
+        // ======================================= TMA producer =======================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, n_qt * Cfg::TILE_BYTES);
+            for (int i = 0; i < n_qt; ++i)
+                for (int c = 0; c < Cfg::NBOX; ++c)
+                    tma_load_3d(sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_q, q_full,
+                                h * HD + c * 64, q0 + i * QT, b, kEvictFirst);
+            for (int j = 0; j < n_kv; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(k_empty(s), ph ^ 1, 10);
+                mbar_arrive_expect_tx(k_full(s), Cfg::TILE_BYTES);
+                for (int c = 0; c < Cfg::NBOX; ++c)
+                    tma_load_3d(sbase + Cfg::K_OFF + s * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_k, k_full(s),
+                                h * HD + c * 64, j * KT, b, kEvictLast);
+                mbar_wait(v_empty(s), ph ^ 1, 11);
+                mbar_arrive_expect_tx(v_full(s), Cfg::TILE_BYTES);
+                for (int c = 0; c < Cfg::NBOX; ++c)
+                    tma_load_3d(sbase + Cfg::V_OFF + s * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_v, v_full(s),
+                                h * HD + c * 64, j * KT, b, kEvictLast);
+            }
+        }
+    } else if (warp == 9) {
+        // ======================================= MMA issuer =======================================
+        if (lane == 0) {
+            // S_i(j) = Q_i . K_j^T : M=128, N=keys of the tile, K=HD, both operands K-major
+            auto issue_s = [&](int i, int j) {
+                const int keys = (j == n_kv - 1) ? tail16 : KT;
+                const uint32_t idesc = umma_idesc_bf16(QT, keys);
+                const uint32_t qa = sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES;
+                const uint32_t ka = sbase + Cfg::K_OFF + (j & 1) * Cfg::TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t off = (k >> 2) * Cfg::BOX_BYTES + (k & 3) * 32;
+                    umma_bf16_ss<1>(tmem + Cfg::TM_S + 128 * i, umma_desc_kmajor_sw128(qa + off),
+                                    umma_desc_kmajor_sw128(ka + off), idesc, k != 0);
+                }
+            };
+            // O_i += P_i(j) . V_j : M=128, N=HD, K=keys; A = P in TMEM (bf16 pairs), B = V MN-major
+            auto issue_pv = [&](int i, int j) {
+                const int keys = (j == n_kv - 1) ? tail16 : KT;
+                constexpr uint32_t idesc = umma_idesc_bf16(QT, HD, 0, 1);
+                const uint32_t va = sbase + Cfg::V_OFF + (j & 1) * Cfg::TILE_BYTES;
+                for (int k = 0; k < keys / 16; ++k) {
+                    umma_bf16_ts(tmem + Cfg::TM_O + HD * i, tmem + Cfg::TM_S + 128 * i + 8 * k,
+                                 umma_desc_mnmajor_sw128(va + k * 2048, Cfg::BOX_BYTES), idesc, (j | k) != 0);
+                }
+            };
+            mbar_wait(q_full, 0, 20);
+            mbar_wait(k_full(0), 0, 21);
+            tc_fence_after();
+            for (int i = 0; i < n_qt; ++i) {
+                issue_s(i, 0);
+                umma_commit(s_full(i));
+            }
+            umma_commit(k_empty(0));
+            for (int j = 0; j < n_kv; ++j) {
+                const bool more = j + 1 < n_kv;
+                mbar_wait(v_full(j & 1), (j >> 1) & 1, 22);
+                if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1, 23);
+                for (int i = 0; i < n_qt; ++i) {
+                    mbar_wait(p_full(i), j & 1, 24);
+                    tc_fence_after();
+                    issue_pv(i, j);
+                    if (i == n_qt - 1) umma_commit(v_empty(j & 1));
+                    if (more) {
+                        issue_s(i, j + 1);
+                        umma_commit(s_full(i));
+                    } else {
+                        umma_commit(o_full(i));
+                    }
+                }
+                if (more) umma_commit(k_empty((j + 1) & 1));
+            }
+        }
+    } else {
+        // ======================================= softmax =======================================
+        const int i = warp >> 2;                        // query tile of this warpgroup
+        const int quarter = warp & 3;
+        if (i < n_qt) {
+            const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+            const uint32_t t_s = tmem + Cfg::TM_S + 128 * i + lane_off;
+            const uint32_t t_o = tmem + Cfg::TM_O + HD * i + lane_off;
+            const int qrow = q0 + i * QT + quarter * 32 + lane;
+            float m_used = -INFINITY, l_sum = 0.f;
+            for (int j = 0; j < n_kv; ++j) {
+                const int keys = (j == n_kv - 1) ? tail : KT;          // valid keys
+                const int keys16 = (keys + 15) & ~15;
+                mbar_wait(s_full(i), j & 1, 30);
+                tc_fence_after();
+                uint32_t sv[128];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c * 32 < keys16) tmem_ld_32x32b_x32(t_s + c * 32, &sv[c * 32]);
+                tmem_ld_wait();
+                if (keys < KT) {
+#pragma unroll
+                    for (int c = 0; c < 128; ++c)
+                        if (c >= keys) sv[c] = 0xff800000u;   // -inf: masked (or never written) key
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                // lazy rescale: keep the stale reference max unless it grows by more than 2^8
+                const float m_new = fmaxf(m_used, mx);
+                const bool grow = (m_new - m_used) * p.scale_log2 > 8.0f;
+                if (j == 0) {
+                    m_used = m_new;
+                } else if (__any_sync(0xffffffffu, grow)) {
+                    const float alpha = grow ? exp2f((m_used - m_new) * p.scale_log2) : 1.0f;
+                    if (grow) m_used = m_new;
+                    l_sum *= alpha;
+#pragma unroll 1
+                    for (int c = 0; c < HD / 16; ++c) {
+                        uint32_t ov[16];
+                        tmem_ld_32x32b_x16(t_o + c * 16, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) ov[t] = __float_as_uint(__uint_as_float(ov[t]) * alpha);
+                        tmem_st_32x32b_x16(t_o + c * 16, ov);
+                    }
+                    tmem_st_wait();
+                }
+                const float mb = m_used * p.scale_log2;
+                float rs = 0.f;
+                // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 < keys16) {
+                        uint32_t pw[16];
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const float e0 = exp2f(fmaf(__uint_as_float(sv[c * 32 + 2 * t]), p.scale_log2, -mb));
+                            const float e1 = exp2f(fmaf(__uint_as_float(sv[c * 32 + 2 * t + 1]), p.scale_log2, -mb));
+                            rs += e0 + e1;
+                            pw[t] = pack_bf16(e0, e1);
+                        }
+                        tmem_st_32x32b_x16(t_s + c * 16, pw);
+                    }
+                }
+                l_sum += rs;
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(p_full(i));
+            }
+            // ---- epilogue: O / l -> bf16, token-major
+            mbar_wait(o_full(i), 0, 31);
+            tc_fence_after();
+            const float inv = 1.0f / l_sum;
+            __nv_bfloat16* orow = p.out + ((int64_t)b * p.L + qrow) * p.ldo + h * HD;
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t ov[32];
+                tmem_ld_32x32b_x32(t_o + c * 32, ov);
+                tmem_ld_wait();
+                if (qrow < p.L) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        uint4 w;
+                        w.x = pack_bf16(__uint_as_float(ov[8 * t + 0]) * inv, __uint_as_float(ov[8 * t + 1]) * inv);
+                        w.y = pack_bf16(__uint_as_float(ov[8 * t + 2]) * inv, __uint_as_float(ov[8 * t + 3]) * inv);
+                        w.z = pack_bf16(__uint_as_float(ov[8 * t + 4]) * inv, __uint_as_float(ov[8 * t + 5]) * inv);
+                        w.w = pack_bf16(__uint_as_float(ov[8 * t + 6]) * inv, __uint_as_float(ov[8 * t + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + 8 * t) = w;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem, 512);
+    }
+}
+
+template <int HD>
+static int launch_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                            int H, float scale, cudaStream_t stream) {
+    using Cfg = AttnCfg<HD>;
+    CUtensorMap mq, mk, mv;
+    const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int st;
+    if ((st = make_tmap(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, strides, box))) return st;
+    if ((st = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box))) return st;
+    if ((st = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box))) return st;
+    auto kern = attention_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+        MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    AttnParams p;
+    p.out = (__nv_bfloat16*)out;
+    p.ldo = ldo;
+    p.L = L; p.H = H; p.B = B;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    const int q_pairs = (L + 2 * QT - 1) / (2 * QT);
+    kern<<<B * H * q_pairs, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, p);
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace mmada
+
+using namespace mmada;
+
+extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
+                                    int B, int L, int H, int head_dim, float scale, void* stream) {
+    if (!q || !k || !v || !out || B <= 0 || L <= 0 || H <= 0) return kBadArgument;
+    if ((ld % 8) || (ldo % 8)) return kUnsupportedShape;
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return kBadArgument;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (head_dim == 128) return launch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+    if (head_dim == 64) return launch_attention<64>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+    return kUnsupportedShape;
+}

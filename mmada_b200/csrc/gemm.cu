@@ -1,0 +1,359 @@
+// tcgen05 / TMEM / TMA GEMM for the LLaDA block projections and the restricted lm_head.
+//
+//   D[M,N] = A[M,K] . B[N,K]^T      A, B bf16 row-major (K contiguous), fp32 accumulation in TMEM
+//
+// replaces the nn.Linear calls of the reference's LLaDALlamaBlock
+// (/root/reference/models/modeling_llada.py:901-903 q/k/v_proj, :724 attn_out, :924 ff_proj/up_proj,
+//  :930 ff_out, :1362 transformer.ff_out), each a cuBLAS GEMM there.
+//
+// Structure (one persistent CTA, or CTA pair, per SM):
+//   warp 0      TMA producer: A and B k-blocks (64 columns = one 128-byte swizzle row) into a ring of
+//               shared-memory stages, signalled through mbarriers
+//   warp 1      allocates TMEM; one lane issues tcgen05.mma (UMMA 128x256x16, or 256x256x16 with
+//               cta_group::2) into one of two 256-column accumulator stages; tcgen05.commit releases
+//               smem stages and publishes finished accumulators
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (one warp per 32-lane quarter), apply the fused
+//               epilogue, store to global; overlaps with the next tile's MMAs
+//
+// Epilogues: bf16 store | fp32 store | fp32 residual add (x + acc) | SwiGLU silu(gate)*up with gate and
+// up interleaved in 128-row blocks of B | bf16 store with per-column bias.
+#include "common.cuh"
+#include "host_utils.h"
+#include "../../include/mmada_b200.h"
+
+namespace mmada {
+
+constexpr int BK = 64;          // k-block: 64 bf16 = 128 bytes = one swizzle row
+constexpr int BM = 128;         // A rows per CTA
+constexpr int BN = 256;         // accumulator columns per tile
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_M = 8;      // rasterisation: tiles walk GROUP_M m-tiles before the next n-tile
+
+struct GemmParams {
+    void* out;
+    const void* aux;     // residual (fp32, ld = ldo) or bias (fp32[N])
+    int64_t ldo;
+    int M, N, K;
+    int num_m_tiles, num_n_tiles;
+};
+
+template <int CG>
+struct GemmCfg {
+    static constexpr int LOAD_N = BN / CG;                     // B rows loaded per CTA
+    static constexpr int A_BYTES = BM * BK * 2;                // 16 KiB
+    static constexpr int B_BYTES = LOAD_N * BK * 2;            // 32 / 16 KiB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = CG == 1 ? 4 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int& mt, int& nt) {
+    const int per_group = GROUP_M * num_n_tiles;
+    const int g = idx / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsize = min(GROUP_M, num_m_tiles - first_m);
+    const int r = idx - g * per_group;
+    mt = first_m + r % gsize;
+    nt = r / gsize;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// one 32-column chunk of one accumulator row
+template <int EPI>
+__device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int col0, const uint32_t (&v)[32]) {
+    if (row >= p.M) return;
+    const int ncols = min(32, p.N - col0);
+    if (ncols <= 0) return;
+    if constexpr (EPI == MMADA_EPI_BF16 || EPI == MMADA_EPI_BIAS_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldo + col0;
+        const float* bias = reinterpret_cast<const float*>(p.aux);
+        if (ncols == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    f[t] = __uint_as_float(v[8 * j + t]);
+                    if constexpr (EPI == MMADA_EPI_BIAS_BF16) f[t] += __ldg(bias + col0 + 8 * j + t);
+                }
+                uint4 w = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                     pack_bf16(f[6], f[7]));
+                *reinterpret_cast<uint4*>(o + 8 * j) = w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+                if (t < ncols) {
+                    float f = __uint_as_float(v[t]);
+                    if constexpr (EPI == MMADA_EPI_BIAS_BF16) f += __ldg(bias + col0 + t);
+                    o[t] = __float2bfloat16_rn(f);
+                }
+        }
+    } else {  // fp32 store, optional residual
+        float* o = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldo + col0;
+        const float* r = reinterpret_cast<const float*>(p.aux) + (int64_t)row * p.ldo + col0;
+        if (ncols == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                if constexpr (EPI == MMADA_EPI_RESID_F32) {
+                    float4 b = *reinterpret_cast<const float4*>(r + 4 * j);
+                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
+                *reinterpret_cast<float4*>(o + 4 * j) = a;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+                if (t < ncols) {
+                    float f = __uint_as_float(v[t]);
+                    if constexpr (EPI == MMADA_EPI_RESID_F32) f += r[t];
+                    o[t] = f;
+                }
+        }
+    }
+}
+
+template <int CG, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+    using Cfg = GemmCfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+    // barrier layout (8 bytes each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8 * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8 * (Cfg::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8 * (2 * Cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8 * (2 * Cfg::STAGES + 2 + a); };
+    const uint32_t tmem_ptr_addr = bar_base + 8 * (2 * Cfg::STAGES + 4);
+    volatile uint32_t* tmem_ptr_smem =
+        reinterpret_cast<volatile uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool leader = cta_rank == 0;
+    const int num_clusters = gridDim.x / CG;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), CG);      // one arrival per producing CTA (+ transaction bytes)
+            mbar_init(empty_bar(s), 1);      // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);          // one tcgen05.commit
+            mbar_init(tempty_bar(a), 4 * CG);    // one arrival per epilogue warp of every CTA
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<CG>(tmem_ptr_addr, 512);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            const uint32_t full0 = CG == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);   // leader's barriers
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                int mt, nt;
+                tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+                const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
+                const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1, 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+                    if constexpr (CG == 1) {
+                        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                        tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
+                        tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n0);
+                    } else {
+                        const uint32_t fb = full0 + 8 * stage;
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
+                        else mbar_arrive_cluster(fb);
+                        tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0);
+                        tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle row (encoded >> 4)
+                        umma_bf16_ss<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if constexpr (CG == 1) umma_commit(empty_bar(stage));
+                    else umma_commit_2sm(empty_bar(stage), 0x3);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if constexpr (CG == 1) umma_commit(tfull_bar(acc));
+                else umma_commit_2sm(tfull_bar(acc), 0x3);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32)
+        const uint32_t tempty0 = CG == 2 ? mapa_u32(tempty_bar(0), 0) : tempty_bar(0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            int mt, nt;
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+            const int row = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase, 4);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            if constexpr (EPI == MMADA_EPI_SWIGLU_BF16) {
+                // columns [0,128) = gate, [128,256) = up for output columns nt*128 + [0,128)
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldo + nt * (BN / 2);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 32, g);
+                    tmem_ld_32x32b_x32(t_addr + BN / 2 + c * 32, u);
+                    tmem_ld_wait();
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                f[q] = silu_f(__uint_as_float(g[8 * j + q])) * __uint_as_float(u[8 * j + q]);
+                            *reinterpret_cast<uint4*>(o + c * 32 + 8 * j) = make_uint4(
+                                pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 32, v);
+                    tmem_ld_wait();
+                    store_chunk<EPI>(p, row, nt * BN + c * 32, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 1) mbar_arrive(tempty_bar(acc));
+                else mbar_arrive_cluster(tempty0 + 8 * acc);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    // teardown: everyone done with TMEM (and, for pairs, the peer done with our smem / barriers)
+    __syncwarp();
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, 512);
+    }
+}
+
+template <int CG, int EPI>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<CG>;
+    auto kern = gemm_kernel<CG, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    int clusters = num_sms() / CG;
+    if (clusters > num_tiles) clusters = num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MMADA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, p));
+    return kOk;
+}
+
+template <int CG>
+static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+    switch (epi) {
+        case MMADA_EPI_BF16: return launch_gemm<CG, MMADA_EPI_BF16>(ma, mb, p, s);
+        case MMADA_EPI_F32: return launch_gemm<CG, MMADA_EPI_F32>(ma, mb, p, s);
+        case MMADA_EPI_RESID_F32: return launch_gemm<CG, MMADA_EPI_RESID_F32>(ma, mb, p, s);
+        case MMADA_EPI_SWIGLU_BF16: return launch_gemm<CG, MMADA_EPI_SWIGLU_BF16>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_BF16: return launch_gemm<CG, MMADA_EPI_BIAS_BF16>(ma, mb, p, s);
+    }
+    return kBadArgument;
+}
+
+}  // namespace mmada
+
+using namespace mmada;
+
+extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                               const void* aux, int M, int N, int K, int epilogue, int cta_group, void* stream) {
+    if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return kBadArgument;
+    if ((lda % 8) || (ldb % 8) || (K % 8)) return kUnsupportedShape;        // 16-byte global strides for TMA
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return kBadArgument;
+    if (epilogue == MMADA_EPI_SWIGLU_BF16 && (N % BN)) return kUnsupportedShape;
+    if ((epilogue == MMADA_EPI_RESID_F32 || epilogue == MMADA_EPI_BIAS_BF16) && !aux) return kBadArgument;
+    if (cta_group != 1 && cta_group != 2) return kBadArgument;
+    CUtensorMap ma, mb;
+    int st = make_tmap_bf16_2d(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (st) return st;
+    st = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(BN / cta_group));
+    if (st) return st;
+    GemmParams p;
+    p.out = out;
+    p.aux = aux;
+    p.ldo = ldo;
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
+    p.num_n_tiles = (N + BN - 1) / BN;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return cta_group == 1 ? dispatch_epi<1>(epilogue, ma, mb, p, s) : dispatch_epi<2>(epilogue, ma, mb, p, s);
+}

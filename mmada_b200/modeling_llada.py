@@ -1,0 +1,191 @@
+"""LLaDA mask predictor on the B200 kernels — host-side mirror of the reference's
+``LLaDAModelLM`` (/root/reference/models/modeling_llada.py:1382-1450 -> LLaDAModel.forward :1161-1366
+-> LLaDALlamaBlock.forward :886-934) for the configuration MMaDA uses: llama blocks, RMSNorm, RoPE,
+SiLU-gated MLP, no biases, untied output head, no KV cache, fully bidirectional attention (the
+``attention_bias`` argument is accepted and ignored exactly like the reference ignores it, Q1).
+
+Data layout in HBM (M = batch * seq_len token rows):
+  x      fp32 [M, d]        residual stream (fp32 instead of the reference's bf16: costs 2x bytes on a
+                            stream read twice per layer, buys margin against the fp32 reference)
+  xn     bf16 [M, d]        RMSNorm output = A operand of the next GEMM
+  qkv    bf16 [M, 3d]       fused q|k|v projection (weights concatenated at load time), RoPE in place
+  att    bf16 [M, d]        attention output, token-major
+  h      bf16 [M, ffn]      silu(ff_proj)*up_proj, produced by the GEMM epilogue (weights interleaved)
+Weights are bf16, [out, in] like nn.Linear; norm weights fp32.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+_P = "model.transformer."
+
+
+@dataclass
+class LLaDAConfig:
+    """The subset of the reference's ModelConfig (models/configuration_llada.py:129-384) the path uses."""
+    d_model: int = 4096
+    n_heads: int = 32
+    n_layers: int = 32
+    mlp_hidden_size: int = 12288
+    vocab_size: int = 134656
+    rope_theta: float = 500000.0
+    rms_norm_eps: float = 1e-5
+    max_sequence_length: int = 4096
+    mask_token_id: int = 126336
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "LLaDAConfig":
+        return cls(**{k: d[k] for k in cls.__dataclass_fields__ if k in d})
+
+    @property
+    def head_dim(self) -> int:
+        return self.d_model // self.n_heads
+
+
+def interleave_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor, block: int = 128) -> torch.Tensor:
+    """[ffn, d] x2 -> [2*ffn, d] with rows alternating in blocks of 128: gate block j, up block j.
+    One 256-column accumulator tile of the GEMM then holds gate and up for the same 128 outputs."""
+    ffn, d = w_gate.shape
+    assert ffn % block == 0, "mlp_hidden_size must be a multiple of 128"
+    g = w_gate.view(ffn // block, block, d)
+    u = w_up.view(ffn // block, block, d)
+    return torch.stack([g, u], dim=1).reshape(2 * ffn, d).contiguous()
+
+
+class CausalLMOutput:
+    """Minimal stand-in for transformers' CausalLMOutputWithPast: `.logits`."""
+
+    def __init__(self, logits: torch.Tensor):
+        self.logits = logits
+
+
+@dataclass
+class _Layer:
+    attn_norm: torch.Tensor
+    wqkv: torch.Tensor
+    attn_out: torch.Tensor
+    ff_norm: torch.Tensor
+    w_gate_up: torch.Tensor
+    ff_out: torch.Tensor
+
+
+class LLaDAModelLM:
+    def __init__(self, config: LLaDAConfig, device="cuda"):
+        self.config = config
+        self.device = torch.device(device)
+        self.layers: List[_Layer] = []
+        self.wte: Optional[torch.Tensor] = None
+        self.ln_f: Optional[torch.Tensor] = None
+        self.head: Optional[torch.Tensor] = None
+        self._rope = None
+        self.cta_group = 2
+        self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
+
+    # ---- weights ---------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> "LLaDAModelLM":
+        """``sd`` uses the reference's key names."""
+        c, dev = self.config, self.device
+
+        def w(k):
+            return sd[k].to(device=dev, dtype=torch.bfloat16).contiguous()
+
+        def n(k):
+            return sd[k].to(device=dev, dtype=torch.float32).contiguous()
+
+        self.wte = w(_P + "wte.weight")
+        self.layers = []
+        for i in range(c.n_layers):
+            b = f"{_P}blocks.{i}."
+            wqkv = torch.cat([w(b + "q_proj.weight"), w(b + "k_proj.weight"), w(b + "v_proj.weight")], 0).contiguous()
+            self.layers.append(_Layer(n(b + "attn_norm.weight"), wqkv, w(b + "attn_out.weight"), n(b + "ff_norm.weight"),
+                                      interleave_gate_up(w(b + "ff_proj.weight"), w(b + "up_proj.weight")),
+                                      w(b + "ff_out.weight")))
+        self.ln_f = n(_P + "ln_f.weight")
+        self.head = w(_P + "ff_out.weight")
+        return self
+
+    def init_random(self, seed: int = 0, std_scale: float = 1.0) -> "LLaDAModelLM":
+        """Random weights generated on the device (benchmarks; no checkpoint is available offline).
+        Scales follow the reference's 'mitchell' init (modeling_llada.py:106-110)."""
+        c, dev = self.config, self.device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        d, f = c.d_model, c.mlp_hidden_size
+
+        def rnd(shape, std):
+            t = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+            t.normal_(0.0, std * std_scale, generator=g)
+            return t
+
+        self.wte = rnd((c.vocab_size, d), d ** -0.5)
+        self.layers = []
+        for i in range(c.n_layers):
+            r = (2 * (i + 1)) ** -0.5
+            self.layers.append(_Layer(torch.ones(d, device=dev), rnd((3 * d, d), d ** -0.5), rnd((d, d), r * d ** -0.5),
+                                      torch.ones(d, device=dev), rnd((2 * f, d), d ** -0.5), rnd((d, f), r * f ** -0.5)))
+        self.ln_f = torch.ones(d, device=dev)
+        self.head = rnd((c.vocab_size, d), d ** -0.5)
+        return self
+
+    def _rope_tables(self, seq_len: int):
+        # exactly the reference's table construction (modeling_llada.py:388-394), on the device
+        if self._rope is None or self._rope[0].shape[0] < seq_len:
+            hd = self.config.head_dim
+            n = max(seq_len, 2048)
+            inv_freq = 1.0 / (self.config.rope_theta ** (torch.arange(0, hd, 2, device=self.device, dtype=torch.float) / hd))
+            seq = torch.arange(n, device=self.device, dtype=torch.float)
+            freqs = torch.einsum("i , j -> i j", seq, inv_freq)
+            self._rope = (freqs.sin().contiguous(), freqs.cos().contiguous())
+        return self._rope
+
+    # ---- forward ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def hidden_states(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """fp32 residual stream after the last block, [B*L, d] (before ln_f)."""
+        c = self.config
+        B, L = input_ids.shape
+        sin, cos = self._rope_tables(L)
+        x = ops.embed(input_ids.to(self.device), self.wte)
+        M = B * L
+        xn = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
+        qkv = torch.empty((M, 3 * c.d_model), dtype=torch.bfloat16, device=self.device)
+        att = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
+        h = torch.empty((M, c.mlp_hidden_size), dtype=torch.bfloat16, device=self.device)
+        cg = self.cta_group
+        for ly in self.layers:
+            ops.rmsnorm(x, ly.attn_norm, c.rms_norm_eps, out=xn)
+            ops.gemm(xn, ly.wqkv, ops.EPI_BF16, out=qkv, cta_group=cg)
+            ops.rope_inplace(qkv, sin, cos, c.d_model, c.head_dim, L)
+            ops.attention(qkv, B, L, c.n_heads, c.head_dim, out=att)
+            ops.gemm(att, ly.attn_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
+            ops.rmsnorm(x, ly.ff_norm, c.rms_norm_eps, out=xn)
+            ops.gemm(xn, ly.w_gate_up, ops.EPI_SWIGLU_BF16, out=h, cta_group=cg)
+            ops.gemm(h, ly.ff_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
+        self.kernel_launches += 1 + 8 * len(self.layers)
+        return x
+
+    @torch.no_grad()
+    def logits_rows(self, input_ids: torch.Tensor, rows: Optional[torch.Tensor], col_lo: int = 0,
+                    col_hi: Optional[int] = None) -> torch.Tensor:
+        """fp32 logits for the token rows ``rows`` (int32 indices into the flattened [B*L] rows; None = all)
+        and vocabulary columns [col_lo, col_hi): ln_f and the output head run on those rows only."""
+        c = self.config
+        x = self.hidden_states(input_ids)
+        xn = ops.rmsnorm(x, self.ln_f, c.rms_norm_eps, rows=rows)
+        col_hi = c.vocab_size if col_hi is None else col_hi
+        self.kernel_launches += 2
+        return ops.gemm(xn, self.head[col_lo:col_hi], ops.EPI_F32, cta_group=self.cta_group)
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_bias=None, **_ignored) -> CausalLMOutput:
+        """Drop-in ``model(input_ids, attention_bias=...).logits`` -> (B, L, V) fp32.  ``attention_bias``
+        is ignored, as in the reference (modeling_llada.py:711-718 passes attn_mask=None)."""
+        B, L = input_ids.shape
+        lg = self.logits_rows(input_ids, None)
+        return CausalLMOutput(lg.view(B, L, -1))
+
+    __call__ = forward

@@ -1,0 +1,137 @@
+"""Thin Python wrappers: torch tensors in, raw pointers over the C ABI, work enqueued on torch's
+current CUDA stream.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_BF16, EPI_BIAS_BF16 = range(5)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.MMadaKernelError(f"{name} must be a CUDA tensor (mmada_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Optional[torch.Tensor] = None,
+         aux: Optional[torch.Tensor] = None, cta_group: int = 2) -> torch.Tensor:
+    """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 with contiguous K."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU_BF16 else N
+    if out is None:
+        dt = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32) else torch.bfloat16
+        out = torch.empty((M, n_out), dtype=dt, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    if epilogue == EPI_RESID_F32:
+        assert aux is not None and aux.dtype == torch.float32 and aux.stride(0) == out.stride(0)
+    _lib.call("mmada_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+              _ptr(aux), M, N, K, epilogue, cta_group, _stream())
+    return out
+
+
+def embed(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    _chk(ids, torch.int64, "ids"); _chk(table, torch.bfloat16, "table")
+    ids = ids.contiguous().view(-1)
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=ids.device)
+    _lib.call("mmada_embed_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), ids.numel(), table.shape[1],
+              table.shape[0], _stream())
+    return out
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, rows: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, torch.float32, "x"); _chk(weight, torch.float32, "weight")
+    assert x.dim() == 2 and x.is_contiguous()
+    m_out = x.shape[0] if rows is None else rows.numel()
+    if rows is not None:
+        _chk(rows, torch.int32, "rows")
+    if out is None:
+        out = torch.empty((m_out, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    _lib.call("mmada_rmsnorm_bf16", x.data_ptr(), weight.data_ptr(), out.data_ptr(), _ptr(rows), m_out, x.shape[1],
+              float(eps), _stream())
+    return out
+
+
+def rope_inplace(qkv: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, d_model: int, head_dim: int, seq_len: int):
+    _chk(qkv, torch.bfloat16, "qkv"); _chk(sin, torch.float32, "sin"); _chk(cos, torch.float32, "cos")
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and sin.is_contiguous() and cos.is_contiguous()
+    assert sin.shape[-1] == head_dim // 2 and sin.shape[0] >= seq_len
+    _lib.call("mmada_rope_inplace_bf16", qkv.data_ptr(), qkv.stride(0), sin.data_ptr(), cos.data_ptr(), qkv.shape[0],
+              d_model, head_dim, seq_len, _stream())
+    return qkv
+
+
+def attention(qkv: torch.Tensor, batch: int, seq_len: int, n_heads: int, head_dim: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv bf16 [batch*seq_len, 3*d] (q | k | v), returns [batch*seq_len, d]."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    d = n_heads * head_dim
+    assert qkv.shape == (batch * seq_len, 3 * d) and qkv.stride(1) == 1
+    if out is None:
+        out = torch.empty((batch * seq_len, d), dtype=torch.bfloat16, device=qkv.device)
+    es = qkv.element_size()
+    _lib.call("mmada_attention_bf16", qkv.data_ptr(), qkv.data_ptr() + d * es, qkv.data_ptr() + 2 * d * es, qkv.stride(0),
+              out.data_ptr(), out.stride(0), batch, seq_len, n_heads, head_dim, 1.0 / math.sqrt(head_dim), _stream())
+    return out
+
+
+def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch.Tensor, u: torch.Tensor,
+                    known: torch.Tensor, input_ids: Optional[torch.Tensor], img_off: int, tickets: torch.Tensor,
+                    guidance: float, mask_len_raw: float, temperature: float, mask_id: int, text_vocab: int,
+                    want_masking: bool = False):
+    """One fused sampling step (see csrc/sampling.cu).  cond/uncond/q: fp32 [B*N, C]; u fp32 [B, N];
+    known int64 [B, N] (updated in place); input_ids int64 [B, L] (image slice updated in place).
+    Returns (sampled_ids [B,N] int64, selected_probs [B,N] fp32, masking [B,N] bool or None)."""
+    B, N = known.shape
+    C = cond.shape[-1]
+    for t, n in ((cond, "cond"), (q, "q"), (u, "u")):
+        _chk(t, torch.float32, n)
+        assert t.is_contiguous()
+    _chk(known, torch.int64, "known"); _chk(tickets, torch.int32, "tickets")
+    assert known.is_contiguous() and cond.numel() == B * N * C and q.numel() == B * N * C and u.numel() == B * N
+    if uncond is not None:
+        _chk(uncond, torch.float32, "uncond")
+        assert uncond.is_contiguous() and uncond.numel() == cond.numel()
+    ld_ids = 0
+    if input_ids is not None:
+        _chk(input_ids, torch.int64, "input_ids")
+        assert input_ids.stride(1) == 1 and input_ids.shape[0] == B
+        ld_ids = input_ids.stride(0)
+    sampled = torch.empty((B, N), dtype=torch.int64, device=cond.device)
+    sel = torch.empty((B, N), dtype=torch.float32, device=cond.device)
+    masking = torch.empty((B, N), dtype=torch.uint8, device=cond.device) if want_masking else None
+    # python scalars reach the tensor op as fp32 in the reference ((1 + g) * cond, g * uncond, T * gumbel)
+    _lib.call("mmada_t2i_sample_step", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
+              _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking), tickets.data_ptr(),
+              B, N, C, float(1 + guidance), float(guidance), float(mask_len_raw), float(temperature), mask_id,
+              text_vocab, _stream())
+    return sampled, sel, (masking.bool() if want_masking else None)
+
+
+def mask_by_random_topk(mask_len: torch.Tensor, probs: torch.Tensor, u: torch.Tensor, temperature: float) -> torch.Tensor:
+    _chk(probs, torch.float32, "probs"); _chk(u, torch.float32, "u")
+    B, N = probs.shape
+    ml = mask_len.to(device=probs.device).long().reshape(-1).contiguous()
+    assert ml.numel() == B
+    out = torch.empty((B, N), dtype=torch.uint8, device=probs.device)
+    _lib.call("mmada_mask_by_random_topk", probs.contiguous().data_ptr(), u.contiguous().data_ptr(), ml.data_ptr(),
+              out.data_ptr(), B, N, float(temperature), _stream())
+    return out.bool()
