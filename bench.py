@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the MMaDA t2i masked-diffusion denoising path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                (own arm; torchrun for N > 1)
+  python bench.py --impl reference [--steps K] [--warmup W]          (reference arm: CPU, host cores)
+
+A "step" is one denoising step of ``MMadaModelLM.t2i_generate`` on BASELINE configs[1]:
+MMaDA-8B architecture (32 layers, d=4096, 32 heads, ffn 12288, V=134656), random-init bf16 weights,
+8 synthetic prompts per GPU with CFG 3.5 (16 x 1539 token rows per forward), 1024 image tokens,
+15-step cosine schedule.  K steps are timed as whole generations of 15 steps plus one partial
+generation; images/s = prompts * (K/15) / time.  Prompts are sharded across GPUs (weak scaling,
+8 per GPU), the CFG pair of a prompt stays on one device, no collective inside the loop; the
+end-to-end number adds the host->device copies of the prompts, the token->pixel decode when built,
+the device->host read of the results and the final NCCL all-gather.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(d_model=4096, n_heads=32, n_layers=32, mlp_hidden_size=12288, vocab_size=134656, rope_theta=500000.0,
+          rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
+STEPS_PER_IMAGE, N_IMG, PREFIX, CODEBOOK, GUIDANCE, PROMPTS_PER_GPU = 15, 1024, 513, 8192, 3.5, 8
+METRIC = "t2i_images_per_sec"
+
+
+def algorithmic_flops_per_step(cfg, B, L, N, C):
+    """2*m*n*k for every matmul the semantics require: block GEMMs + attention
+    (4*L^2*d per sequence per layer) + lm_head on the N image rows x C codebook columns, both branches."""
+    d, f, nl = cfg["d_model"], cfg["mlp_hidden_size"], cfg["n_layers"]
+    M = 2 * B * L
+    block = 2.0 * M * (4 * d * d + 3 * d * f) * nl
+    attn = 4.0 * L * L * d * nl * 2 * B
+    head = 2.0 * (2 * B * N) * C * d
+    return block, attn, head
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sustained=j["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], 0, set(), 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1])); pw = max(pw, float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # median over samples under load (upper half: the idle samples before/after drag the median down)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "power_w_max": pw, "samples": len(sm)}
+
+
+# ================================================================================================
+# reference arm / CPU baseline: the oracle restatement (oracle/ — pinned bit-exact to the real
+# reference by oracle/make_goldens.py) timed on the host cores on a bounded sample of the workload
+# ================================================================================================
+def cpu_sample_seconds(threads, reps, warm=1):
+    """One 8B-architecture LLaDA block on one CFG pair (2 x 1539 token rows, fp32) + the restricted
+    head and one sampling step on its 1024 image rows.  Returns (seconds per sample, images/s)."""
+    from oracle import denoise, llada, weights as W
+    torch.set_num_threads(threads)
+    cfg = dict(C2, n_layers=1)
+    g = torch.Generator().manual_seed(0)
+    d, f = cfg["d_model"], cfg["mlp_hidden_size"]
+    p = "model.transformer.blocks.0."
+    sd = {p + "attn_norm.weight": torch.ones(d), p + "ff_norm.weight": torch.ones(d)}
+    for n, shp in (("q_proj", (d, d)), ("k_proj", (d, d)), ("v_proj", (d, d)), ("attn_out", (d, d)),
+                   ("ff_proj", (f, d)), ("up_proj", (f, d)), ("ff_out", (d, f))):
+        sd[p + n + ".weight"] = torch.randn(shp, generator=g) * shp[1] ** -0.5
+    head = torch.randn(CODEBOOK, d, generator=g) * d ** -0.5
+    L = PREFIX + 1 + N_IMG + 1
+    x = torch.randn(2, L, d, generator=g)
+    q = torch.empty(N_IMG, CODEBOOK).exponential_(1, generator=g)
+    u = torch.rand(1, N_IMG, generator=g)
+    known = torch.full((1, N_IMG), 126336, dtype=torch.int64)
+    t_layer, t_tail = [], []
+    with torch.no_grad():
+        for r in range(warm + reps):
+            t0 = time.perf_counter()
+            y = llada.block_forward(x, sd, 0, cfg)
+            t1 = time.perf_counter()
+            h = llada.rms_norm(y[:, -(N_IMG + 1):-1], torch.ones(d), 1e-5)
+            lg = torch.nn.functional.linear(h, head)
+            denoise.t2i_sample_step(lg[:1], lg[1:], GUIDANCE, known, 126336, 500.0, 0.5, q, u)
+            t2 = time.perf_counter()
+            if r >= warm:
+                t_layer.append(t1 - t0); t_tail.append(t2 - t1)
+    tl, tt = sum(t_layer) / len(t_layer), sum(t_tail) / len(t_tail)
+    sec_per_image = STEPS_PER_IMAGE * (C2["n_layers"] * tl + tt)
+    return tl + tt, 1.0 / sec_per_image
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_probe, _ = cpu_sample_seconds(threads, 1, warm=1)
+    reps = max(1, min(args.steps, int(200.0 / max(t_probe, 1e-3))))
+    t0 = time.perf_counter()
+    t_s, ips = cpu_sample_seconds(threads, reps, warm=min(args.warmup, 2))
+    sample = ("1 of 32 LLaDA-8B blocks on one CFG pair (2x1539 token rows, fp32, oracle port of the reference) + "
+              "restricted head + one sampling step on 1024 image rows; images/s extrapolated x32 layers x15 steps")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": reps, "warmup": min(args.warmup, 2), "ms_per_step": t_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MMaDA-8B-arch t2i 512x512, 1024 image tokens, 15 steps, CFG 3.5 (CPU, bounded sample)"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ================================================================================================
+# own arm
+# ================================================================================================
+def run_own(args):
+    import torch.distributed as dist
+    from mmada_b200 import MMadaConfig, MMadaModelLM, ops
+    from mmada_b200.prompting import UniPromptingLike, synthetic_t2i_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfgd = dict(C2)
+    if args.layers:
+        cfgd["n_layers"] = args.layers            # debugging only; reported in config and INVALID as a result
+    B = PROMPTS_PER_GPU
+    model = MMadaModelLM(MMadaConfig.from_dict(cfgd), device=dev).init_random(seed=1234)
+    model.cta_group = args.cta_group
+    up = UniPromptingLike()
+    # prompts are indexed globally; rank r owns prompts [r*B, (r+1)*B)  (results independent of world size)
+    cond_h, unc_h, _, _ = synthetic_t2i_batch(B * world, PREFIX, N_IMG, seed=0)
+    cond_h = cond_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    unc_h = unc_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    L = cond_h.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    vq = None
+    try:
+        from mmada_b200.modeling_magvitv2 import MAGVITv2
+        vq = MAGVITv2(device=dev).init_random(seed=7)
+    except ImportError:
+        vq = None
+
+    def generation(ids_dev, unc_dev, stop=None):
+        return model.t2i_generate(input_ids=ids_dev, uncond_input_ids=unc_dev, guidance_scale=GUIDANCE,
+                                  timesteps=STEPS_PER_IMAGE, seq_len=N_IMG, resolution=PREFIX - 1, generator=gen,
+                                  uni_prompting=up, stop_after_steps=stop)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    unc_d = unc_h.to(dev)
+    # ---- warm-up: W denoising steps (whole generations + one partial)
+    wf, wp = divmod(max(args.warmup, 1), STEPS_PER_IMAGE)
+    for _ in range(wf):
+        generation(cond_h.to(dev), unc_d)
+    if wp:
+        generation(cond_h.to(dev), unc_d, stop=wp)
+    # ---- timed: exactly K denoising steps, inputs resident in HBM
+    K = args.steps
+    full, part = divmod(K, STEPS_PER_IMAGE)
+    inputs = [cond_h.to(dev) for _ in range(full + (1 if part else 0))]
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_EVENTS = [] if not args.no_kernel_events else None
+    launches0 = model.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(full):
+        generation(inputs[i], unc_d)
+    if part:
+        generation(inputs[full], unc_d, stop=part)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.kernel_launches - launches0
+    gemm_events, ops.GEMM_EVENTS = ops.GEMM_EVENTS, None
+    clocks = sampler.stop() if rank == 0 else None
+    images = B * world * K / STEPS_PER_IMAGE
+    value = images / (ms / 1e3)
+
+    # ---- end to end through the public API, host buffers in, host results out
+    G = max(1, K // STEPS_PER_IMAGE)
+    out_h = torch.empty((B, 3, 512, 512) if vq is not None else (B, N_IMG),
+                        dtype=torch.uint8 if vq is not None else torch.int64).pin_memory()
+    barrier()
+    t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e0.record()
+    for _ in range(G):
+        ids_d = cond_h.to(dev, non_blocking=True)
+        un_d = unc_h.to(dev, non_blocking=True)
+        codes = generation(ids_d, un_d)
+        if vq is not None:
+            res = vq.decode_code_uint8(codes)
+        else:
+            res = codes
+        if world > 1:
+            gathered = [torch.empty_like(res) for _ in range(world)]
+            dist.all_gather(gathered, res)
+        out_h.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t_e0.elapsed_time(t_e1))
+    e2e = B * world * G / (ms_e2e / 1e3)
+    h2d = (cond_h.numel() + unc_h.numel()) * 8 / STEPS_PER_IMAGE
+    d2h = out_h.numel() * out_h.element_size() / STEPS_PER_IMAGE
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed live on the launching stream
+    pk = peaks()
+    roof = None
+    if gemm_events:
+        tot_ms = sum(a.elapsed_time(b) for a, b, *_ in gemm_events)
+        tot_fl = sum(2.0 * M * N * Kk for _, _, M, N, Kk, _ in gemm_events)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        by = {}
+        for a, b, M, N, Kk, ep in gemm_events:
+            k = f"{M}x{N}x{Kk}/epi{ep}"
+            t, n, _ = by.get(k, (0.0, 0, 0.0))
+            by[k] = (t + a.elapsed_time(b), n + 1, 2.0 * M * N * Kk)
+        roof = {"bound": "tensor", "kernel": f"mmada::gemm_kernel<{args.cta_group},*> (tcgen05 UMMA 256x256x16, TMA, TMEM)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "peak_source": pk["source"] + " cuBLAS bf16 sustained", "traffic": None,
+                "launches": len(gemm_events), "avg_launch_ms": tot_ms / len(gemm_events),
+                "share_of_step": tot_ms / ms,
+                "per_shape": {k: {"ms": t / n, "tflops": fl / (t / n * 1e-3) / 1e12} for k, (t, n, fl) in by.items()}}
+    blk, att, head = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
+    step_tf = (blk + att + head) / 1e12
+    ms_step = ms / K
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            t_s, ips = cpu_sample_seconds(os.cpu_count() or 1, 2)
+            cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "1 of 32 LLaDA-8B blocks on one CFG pair (2x1539 rows, fp32, oracle port) + restricted head + "
+                             "sampling step; extrapolated x32 layers x15 steps"}
+        except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "MMaDA-8B-arch t2i 512x512: 1024 image tokens, 15 steps, CFG 3.5, 8 prompts/GPU "
+                                   "(16x1539 token rows per forward), random-init bf16 weights",
+                       "n_layers": cfgd["n_layers"], "prompts_per_gpu": B, "seq_len": L, "parallelism": f"prompt-shard x{world}",
+                       "l2": "inputs_exceed_l2 (16 GB of weights streamed per step)", "decode_in_e2e": vq is not None},
+            "tokens_per_sec": value * N_IMG, "algorithmic_tflop_per_step": step_tf,
+            "model_tflops_per_gpu": step_tf / (ms_step * 1e-3), "frac_of_bf16_sustained_peak": step_tf / (ms_step * 1e-3) / pk["tf_sustained"],
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "generations": G},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=15)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--cta-group", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=0, help="debug: override layer count (result is then not the benchmark)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-events", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ class MMadaModelLM(LLaDAModelLM):
         text_vocab = len(uni_prompting.text_tokenizer)
         noise = kwargs.get("noise", None)
         trace = kwargs.get("trace", None)
+        stop_after = kwargs.get("stop_after_steps", None)     # benchmarking hook: cut the loop short
         N, C = seq_len, codebook_size
         dev = self.device
         caller_ids = input_ids
@@ -77,6 +78,8 @@ class MMadaModelLM(LLaDAModelLM):
         tickets = torch.zeros(B, dtype=torch.int32, device=dev)
         sampled = None
         for step in range(timesteps):
+            if stop_after is not None and step >= stop_after:
+                break
             model_input[:B] = input_ids
             if cfg:
                 model_input[B:, P:] = input_ids[:, P:]

@@ -12,6 +12,11 @@ from . import _lib
 EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_BF16, EPI_BIAS_BF16 = range(5)
 
 
+#: when set to a list, every GEMM launch appends (start_event, end_event, M, N, K, epilogue) — used by
+#: bench.py to time the dominant kernel live on the launching stream
+GEMM_EVENTS = None
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -42,8 +47,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Option
     assert out.shape == (M, n_out) and out.stride(1) == 1
     if epilogue == EPI_RESID_F32:
         assert aux is not None and aux.dtype == torch.float32 and aux.stride(0) == out.stride(0)
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("mmada_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
               _ptr(aux), M, N, K, epilogue, cta_group, _stream())
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1, M, N, K, epilogue))
     return out
 
 
