@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mmada_b200.h declares; host-side
+logic (prompt layout, weight interleave, schedules, error behaviour without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mmada_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"\bint\s+(mmada_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    from mmada_b200 import _lib
+    lib = _lib.load()
+    fns = _header_functions()
+    assert len(fns) >= 9
+    for f in fns:
+        assert hasattr(lib, f), f"{f} declared in the header but not exported"
+        assert f in _lib.SIGNATURES, f"{f} has no ctypes signature"
+    assert set(_lib.SIGNATURES) <= set(fns), "ctypes table names a function the header does not declare"
+    assert lib.mmada_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import mmada_b200
+    from mmada_b200 import _lib, ops
+    with pytest.raises(_lib.MMadaKernelError):
+        mmada_b200.mask_by_random_topk(torch.tensor([[1.0]]), torch.rand(1, 8))
+    with pytest.raises(_lib.MMadaKernelError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mmada_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(pkg, fn)).read(), flags=re.M), fn
+
+
+def test_schedules_match_reference_tables(golden):
+    import mmada_b200 as mb
+    gd = golden("sampling")
+    for N in (64, 256, 1024):
+        for T in (8, 15, 18):
+            got = [float((N * mb.cosine_schedule(torch.tensor(1.0 * (s + 1) / T))).floor()) for s in range(T)]
+            assert got == list(gd[f"cos_{N}_{T}"])
+    for name in ("linear", "pow2", "sigmoid"):
+        f = mb.get_mask_schedule(name)
+        got = np.array([float(f(torch.tensor(t))) for t in np.linspace(0, 1, 11)])
+        assert np.array_equal(got, gd["sched_" + name])
+    with pytest.raises(ValueError):
+        mb.get_mask_schedule("nope")
+
+
+def test_prompt_layout_matches_oracle_generator():
+    from mmada_b200.prompting import RESERVED, t2i_gen_prompt
+    img = torch.full((2, 16), 126336)
+    ids, mask = t2i_gen_prompt([[5, 6, 7], []], img, max_text_len=10)
+    assert ids.shape == (2, 28)
+    assert ids[0].tolist()[:10] == [126093] * 4 + [126088, 126080, 5, 6, 7, 126081]
+    assert ids[1].tolist()[:10] == [126093] * 7 + [126088, 126080, 126081]
+    assert ids[0, 10] == RESERVED["<|soi|>"] and ids[0, -1] == RESERVED["<|eoi|>"]
+    assert mask[0].tolist() == [0] * 4 + [1] * 24
+    # truncation branch
+    ids2, mask2 = t2i_gen_prompt([list(range(20))], img[:1], max_text_len=8)
+    assert ids2.shape == (1, 26) and ids2[0, 7] == 126081 and mask2.sum() == 26
+
+
+def test_interleave_gate_up():
+    from mmada_b200 import interleave_gate_up
+    g = torch.arange(256 * 4, dtype=torch.float32).view(256, 4)
+    u = -g
+    w = interleave_gate_up(g, u)
+    assert w.shape == (512, 4)
+    assert torch.equal(w[:128], g[:128]) and torch.equal(w[128:256], u[:128])
+    assert torch.equal(w[256:384], g[128:]) and torch.equal(w[384:], u[128:])
