@@ -109,78 +109,92 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     if (warp == 8) {
         // ======================================= TMA producer =======================================
-        if (lane == 0) {
+        // the whole warp walks the loop (uniform addresses), one elected lane issues
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, n_qt * Cfg::TILE_BYTES);
             for (int i = 0; i < n_qt; ++i)
                 for (int c = 0; c < Cfg::NBOX; ++c)
                     tma_load_3d(sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_q, q_full,
                                 h * HD + c * 64, q0 + i * QT, b, kEvictFirst);
-            for (int j = 0; j < n_kv; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(k_empty(s), ph ^ 1, 10);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+            const int s = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            mbar_wait(k_empty(s), ph ^ 1, 10);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(k_full(s), Cfg::TILE_BYTES);
                 for (int c = 0; c < Cfg::NBOX; ++c)
                     tma_load_3d(sbase + Cfg::K_OFF + s * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_k, k_full(s),
                                 h * HD + c * 64, j * KT, b, kEvictLast);
-                mbar_wait(v_empty(s), ph ^ 1, 11);
+            }
+            __syncwarp();
+            mbar_wait(v_empty(s), ph ^ 1, 11);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(v_full(s), Cfg::TILE_BYTES);
                 for (int c = 0; c < Cfg::NBOX; ++c)
                     tma_load_3d(sbase + Cfg::V_OFF + s * Cfg::TILE_BYTES + c * Cfg::BOX_BYTES, &map_v, v_full(s),
                                 h * HD + c * 64, j * KT, b, kEvictLast);
             }
+            __syncwarp();
         }
     } else if (warp == 9) {
         // ======================================= MMA issuer =======================================
-        if (lane == 0) {
-            // S_i(j) = Q_i . K_j^T : M=128, N=keys of the tile, K=HD, both operands K-major
-            auto issue_s = [&](int i, int j) {
-                const int keys = (j == n_kv - 1) ? tail16 : KT;
-                const uint32_t idesc = umma_idesc_bf16(QT, keys);
-                const uint32_t qa = sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES;
-                const uint32_t ka = sbase + Cfg::K_OFF + (j & 1) * Cfg::TILE_BYTES;
+        // the whole warp walks the schedule and waits; one elected lane issues MMAs and commits
+        const uint64_t kdesc_hi = umma_desc_kmajor_sw128(0);
+        const uint64_t vdesc_hi = umma_desc_mnmajor_sw128(0, Cfg::BOX_BYTES);
+        // S_i(j) = Q_i . K_j^T : M=128, N=keys of the tile, K=HD, both operands K-major
+        auto issue_s = [&](int i, int j) {
+            const int keys = (j == n_kv - 1) ? tail16 : KT;
+            const uint32_t idesc = umma_idesc_bf16(QT, keys);
+            const uint32_t qa = (sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES) >> 4;
+            const uint32_t ka = (sbase + Cfg::K_OFF + (j & 1) * Cfg::TILE_BYTES) >> 4;
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t off = (k >> 2) * Cfg::BOX_BYTES + (k & 3) * 32;
-                    umma_bf16_ss<1>(tmem + Cfg::TM_S + 128 * i, umma_desc_kmajor_sw128(qa + off),
-                                    umma_desc_kmajor_sw128(ka + off), idesc, k != 0);
-                }
-            };
-            // O_i += P_i(j) . V_j : M=128, N=HD, K=keys; A = P in TMEM (bf16 pairs), B = V MN-major
-            auto issue_pv = [&](int i, int j) {
-                const int keys = (j == n_kv - 1) ? tail16 : KT;
-                constexpr uint32_t idesc = umma_idesc_bf16(QT, HD, 0, 1);
-                const uint32_t va = sbase + Cfg::V_OFF + (j & 1) * Cfg::TILE_BYTES;
-                for (int k = 0; k < keys / 16; ++k) {
-                    umma_bf16_ts(tmem + Cfg::TM_O + HD * i, tmem + Cfg::TM_S + 128 * i + 8 * k,
-                                 umma_desc_mnmajor_sw128(va + k * 2048, Cfg::BOX_BYTES), idesc, (j | k) != 0);
-                }
-            };
-            mbar_wait(q_full, 0, 20);
-            mbar_wait(k_full(0), 0, 21);
-            tc_fence_after();
+            for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t off = ((k >> 2) * Cfg::BOX_BYTES + (k & 3) * 32) >> 4;
+                umma_bf16_ss<1>(tmem + Cfg::TM_S + 128 * i, kdesc_hi | (uint64_t)(qa + off), kdesc_hi | (uint64_t)(ka + off),
+                                idesc, k != 0);
+            }
+        };
+        // O_i += P_i(j) . V_j : M=128, N=HD, K=keys; A = P in TMEM (bf16 pairs), B = V MN-major
+        auto issue_pv = [&](int i, int j) {
+            const int keys = (j == n_kv - 1) ? tail16 : KT;
+            constexpr uint32_t idesc = umma_idesc_bf16(QT, HD, 0, 1);
+            const uint32_t va = (sbase + Cfg::V_OFF + (j & 1) * Cfg::TILE_BYTES) >> 4;
+            for (int k = 0; k < keys / 16; ++k)
+                umma_bf16_ts(tmem + Cfg::TM_O + HD * i, tmem + Cfg::TM_S + 128 * i + 8 * k,
+                             vdesc_hi | (uint64_t)(va + k * (2048 >> 4)), idesc, (j | k) != 0);
+        };
+        mbar_wait(q_full, 0, 20);
+        mbar_wait(k_full(0), 0, 21);
+        tc_fence_after();
+        if (elect_one()) {
             for (int i = 0; i < n_qt; ++i) {
                 issue_s(i, 0);
                 umma_commit(s_full(i));
             }
             umma_commit(k_empty(0));
-            for (int j = 0; j < n_kv; ++j) {
-                const bool more = j + 1 < n_kv;
-                mbar_wait(v_full(j & 1), (j >> 1) & 1, 22);
-                if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1, 23);
-                for (int i = 0; i < n_qt; ++i) {
-                    mbar_wait(p_full(i), j & 1, 24);
-                    tc_fence_after();
+        }
+        __syncwarp();
+        for (int j = 0; j < n_kv; ++j) {
+            const bool more = j + 1 < n_kv;
+            mbar_wait(v_full(j & 1), (j >> 1) & 1, 22);
+            if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1, 23);
+            for (int i = 0; i < n_qt; ++i) {
+                mbar_wait(p_full(i), j & 1, 24);
+                tc_fence_after();
+                if (elect_one()) {
                     issue_pv(i, j);
                     if (i == n_qt - 1) umma_commit(v_empty(j & 1));
                     if (more) {
                         issue_s(i, j + 1);
                         umma_commit(s_full(i));
+                        if (i == n_qt - 1) umma_commit(k_empty((j + 1) & 1));
                     } else {
                         umma_commit(o_full(i));
                     }
                 }
-                if (more) umma_commit(k_empty((j + 1) & 1));
+                __syncwarp();
             }
         }
     } else {

@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // arrive on a barrier given by a shared::cluster address (possibly in the peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -70,9 +70,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return done != 0;
 }
 // Blocking wait with a watchdog: a protocol bug traps (launch fails with an error) instead of
-// hanging the GPU.  `tag` identifies the call site in the message.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
-    if (mbar_try_wait(bar, parity)) return;
+// hanging the GPU.  `tag` identifies the call site in the message.  The slow path is out of line so
+// that the single-thread issue loops stay short.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
 #if MMADA_WATCHDOG
     long long t0 = clock64();
     uint32_t n = 0;
@@ -86,6 +86,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 #else
     while (!mbar_try_wait(bar, parity)) {}
 #endif
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, tag);
+}
+// one elected lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 // ------------------------------------------------------------------------------------------

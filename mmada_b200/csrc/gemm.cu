@@ -147,7 +147,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(full_bar(s), CG);      // one arrival per producing CTA (+ transaction bytes)
+            mbar_init(full_bar(s), 1);       // the leader's arrive.expect_tx (+ transaction bytes of both CTAs)
             mbar_init(empty_bar(s), 1);      // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -167,38 +167,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            const uint32_t full0 = CG == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);   // leader's barriers
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                int mt, nt;
-                tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
-                const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
-                const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1, 1);
-                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + Cfg::A_BYTES;
+        // The whole warp runs the loop (addresses stay in uniform registers); one elected lane issues.
+        const uint32_t full0 = CG == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);   // leader's barriers
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            int mt, nt;
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+            const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
+            const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1, 1);
+                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sb = sa + Cfg::A_BYTES;
+                if (elect_one()) {
                     if constexpr (CG == 1) {
                         mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
                         tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
                         tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n0);
                     } else {
+                        // both CTAs' bytes are accounted on the leader's barrier; the peer's complete_tx may
+                        // precede the leader's expect_tx within the phase (transiently negative tx-count)
                         const uint32_t fb = full0 + 8 * stage;
                         if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
-                        else mbar_arrive_cluster(fb);
                         tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0);
                         tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0);
                     }
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0 && leader) {
+        if (leader) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+            const uint64_t desc_hi = umma_desc_kmajor_sw128(0);          // everything but the start address
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -211,19 +215,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     mbar_wait(full_bar(stage), phase, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+                    const uint64_t adesc = desc_hi | (uint64_t)(sa >> 4);
+                    const uint64_t bdesc = desc_hi | (uint64_t)((sa + Cfg::A_BYTES) >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the swizzle row (encoded >> 4)
-                        umma_bf16_ss<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the swizzle row (encoded >> 4)
+                            umma_bf16_ss<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if constexpr (CG == 1) umma_commit(empty_bar(stage));
+                        else umma_commit_2sm(empty_bar(stage), 0x3);
+                        if (kb == num_kb - 1) {
+                            if constexpr (CG == 1) umma_commit(tfull_bar(acc));
+                            else umma_commit_2sm(tfull_bar(acc), 0x3);
+                        }
                     }
-                    if constexpr (CG == 1) umma_commit(empty_bar(stage));
-                    else umma_commit_2sm(empty_bar(stage), 0x3);
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if constexpr (CG == 1) umma_commit(tfull_bar(acc));
-                else umma_commit_2sm(tfull_bar(acc), 0x3);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
