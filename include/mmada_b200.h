@@ -85,6 +85,25 @@ int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, 
 int mmada_mask_by_random_topk(const float* probs, const float* u_noise, const int64_t* mask_len,
                               uint8_t* masking_out, int B, int N, float temperature, void* stream);
 
+/* ---- text / MMU path: low-confidence remasking ------------------------------------------------
+ * text_sample_rows: per candidate row r (R rows of V fp32 logits): optional CFG mix
+ *   un + (cfg+1)*(l-un) (un_logits may be NULL), Gumbel-max token x0 = argmax exp(l64)/(-log u)^T in
+ *   fp64 (temperature 0 -> plain argmax), and conf = softmax(l64)[x0] in fp64.  u_noise fp64 [R,V]
+ *   supplies the uniforms (parity); NULL draws them in-kernel (Philox4x32-10 keyed by seed,row,col).
+ *   Replaces generate.py:8-19,86,90-96 == models/modeling_mmada.py:49-60,436,441-448.
+ * block_mask_count: cnt[b] = #(x[b, lo:lo+block] == mask_id)           generate.py:76-77,22-28
+ * text_transfer: k = cnt/steps + (step < cnt%steps); among the masked positions of the block pick the k
+ *   largest conf (ties: lower position) and set x[b, lo+p] = x0[b*block+p].  conf_override (fp64
+ *   [B,block], may be NULL) replaces conf ('random' remasking).  generate.py:102-111,30-40        */
+int mmada_text_sample_rows(const float* logits, const float* un_logits, float cfg_scale_plus1,
+                           const double* u_noise, uint64_t seed, float temperature, int R, int V,
+                           int64_t* x0_out, double* conf_out, void* stream);
+int mmada_block_mask_count(const int64_t* x, int64_t ld, int lo, int block, int B, int64_t mask_id,
+                           int32_t* cnt_out, void* stream);
+int mmada_text_transfer(int64_t* x, int64_t ld, int lo, int block, const int64_t* x0, const double* conf,
+                        const double* conf_override, const int32_t* cnt, int steps, int step, int B,
+                        int64_t mask_id, uint8_t* transfer_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

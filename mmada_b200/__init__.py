@@ -7,6 +7,7 @@ generate.py:43).  Everything executes hand-written CUDA kernels from libmmada_b2
 C ABI (include/mmada_b200.h); there is no CPU or PyTorch fallback — importing works without a GPU,
 calling raises.
 """
+from .generate import generate, get_num_transfer_tokens  # noqa: F401
 from .modeling_llada import LLaDAConfig, LLaDAModelLM, interleave_gate_up  # noqa: F401
 from .modeling_mmada import MMadaConfig, MMadaModelLM  # noqa: F401
 from .sampling import (cosine_schedule, get_mask_schedule, linear_schedule, mask_by_random_topk,  # noqa: F401

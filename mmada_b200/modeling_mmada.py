@@ -20,6 +20,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from . import generate as _generate
 from .modeling_llada import CausalLMOutput, LLaDAConfig, LLaDAModelLM
 from .sampling import cosine_schedule
 
@@ -108,3 +109,24 @@ class MMadaModelLM(LLaDAModelLM):
         if caller_ids is not input_ids:
             caller_ids.copy_(input_ids)                                          # keep the in-place contract
         return sampled
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def mmu_generate(self, idx=None, input_embeddings=None, max_new_tokens=128, steps=128, block_length=128,
+                     temperature=0.0, top_k=None, eot_token=None, cfg_scale=0.0, remasking='low_confidence',
+                     mask_id=126336, attention_mask=None, **kwargs):
+        """Reference models/modeling_mmada.py:388-481: the same algorithm as ``generate()``.  ``top_k``,
+        ``input_embeddings`` and ``eot_token`` are accepted and ignored like the reference (Q14)."""
+        return _generate.generate(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
+                                  temperature=temperature, cfg_scale=cfg_scale, remasking=remasking, mask_id=mask_id,
+                                  attention_mask=attention_mask, **kwargs)
+
+    @torch.no_grad()
+    def mmu_generate_fast(self, idx=None, input_embeddings=None, max_new_tokens=128, steps=128, block_length=128,
+                          temperature=0.0, top_k=None, eot_token=None, cfg_scale=0.0, remasking='low_confidence',
+                          mask_id=126336, attention_mask=None, **kwargs):
+        """Reference :483-556: ``mmu_generate`` plus an early exit once every row's block-final token is
+        ``eot_token`` (one device->host read per block, as in the reference)."""
+        return _generate.generate(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
+                                  temperature=temperature, cfg_scale=cfg_scale, remasking=remasking, mask_id=mask_id,
+                                  attention_mask=attention_mask, eot_token=eot_token, **kwargs)

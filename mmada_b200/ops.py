@@ -147,3 +147,47 @@ def mask_by_random_topk(mask_len: torch.Tensor, probs: torch.Tensor, u: torch.Te
     _lib.call("mmada_mask_by_random_topk", probs.contiguous().data_ptr(), u.contiguous().data_ptr(), ml.data_ptr(),
               out.data_ptr(), B, N, float(temperature), _stream())
     return out.bool()
+
+
+def text_sample_rows(logits: torch.Tensor, un_logits: Optional[torch.Tensor], cfg_scale: float, temperature: float,
+                     u_noise: Optional[torch.Tensor] = None, seed: int = 0):
+    """logits fp32 [R, V] -> (x0 int64 [R], conf fp64 [R]); see csrc/textsample.cu."""
+    _chk(logits, torch.float32, "logits")
+    assert logits.dim() == 2 and logits.is_contiguous()
+    R, V = logits.shape
+    if un_logits is not None:
+        _chk(un_logits, torch.float32, "un_logits")
+        assert un_logits.is_contiguous() and un_logits.shape == logits.shape
+    if u_noise is not None:
+        _chk(u_noise, torch.float64, "u_noise")
+        assert u_noise.is_contiguous() and u_noise.shape == logits.shape
+    x0 = torch.empty(R, dtype=torch.int64, device=logits.device)
+    conf = torch.empty(R, dtype=torch.float64, device=logits.device)
+    _lib.call("mmada_text_sample_rows", logits.data_ptr(), _ptr(un_logits), float(cfg_scale + 1), _ptr(u_noise),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, float(temperature), R, V, x0.data_ptr(), conf.data_ptr(), _stream())
+    return x0, conf
+
+
+def block_mask_count(x: torch.Tensor, lo: int, block: int, mask_id: int) -> torch.Tensor:
+    _chk(x, torch.int64, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    cnt = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
+    _lib.call("mmada_block_mask_count", x.data_ptr(), x.stride(0), lo, block, x.shape[0], mask_id, cnt.data_ptr(), _stream())
+    return cnt
+
+
+def text_transfer(x: torch.Tensor, lo: int, block: int, x0: torch.Tensor, conf: Optional[torch.Tensor],
+                  cnt: torch.Tensor, steps: int, step: int, mask_id: int, conf_override: Optional[torch.Tensor] = None,
+                  want_transfer: bool = False):
+    _chk(x, torch.int64, "x"); _chk(x0, torch.int64, "x0"); _chk(cnt, torch.int32, "cnt")
+    B = x.shape[0]
+    assert x0.numel() == B * block and x0.is_contiguous()
+    if conf is not None:
+        _chk(conf, torch.float64, "conf")
+    if conf_override is not None:
+        _chk(conf_override, torch.float64, "conf_override")
+        assert conf_override.is_contiguous() and conf_override.numel() == B * block
+    tr = torch.empty((B, block), dtype=torch.uint8, device=x.device) if want_transfer else None
+    _lib.call("mmada_text_transfer", x.data_ptr(), x.stride(0), lo, block, x0.data_ptr(), _ptr(conf), _ptr(conf_override),
+              cnt.data_ptr(), steps, step, B, mask_id, _ptr(tr), _stream())
+    return tr.bool() if want_transfer else None
