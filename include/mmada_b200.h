@@ -37,10 +37,13 @@ enum {
     MMADA_EPI_RESID_F32 = 2,   /* out fp32 [M,N] = aux fp32 [M,N] (same ld as out; may alias) + acc    */
     MMADA_EPI_SWIGLU_BF16 = 3, /* out bf16 [M,N/2] = silu(gate)*up; B rows interleaved per 128:
                                   rows [256j,256j+128) = ff_proj rows [128j,..), next 128 = up_proj  */
-    MMADA_EPI_BIAS_BF16 = 4    /* out bf16 [M,N] = acc + aux fp32 [N]                                */
+    MMADA_EPI_BIAS_BF16 = 4,   /* out bf16 [M,N] = acc + bias fp32 [N]                               */
+    MMADA_EPI_BIAS_F32 = 5,    /* out fp32 [M,N] = acc + bias                                        */
+    MMADA_EPI_BIAS_RESID_F32 = 6 /* out fp32 [M,N] = acc + bias + aux fp32 [M,N]                      */
 };
 int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
-                    const void* aux, int M, int N, int K, int epilogue, int cta_group, void* stream);
+                    const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
+                    void* stream);
 
 /* ---- HBM-bound block kernels ----------------------------------------------------------------
  * embed:   out fp32 [M,d] = table bf16 [vocab,d][ids[m]]         models/modeling_llada.py:1222
@@ -103,6 +106,34 @@ int mmada_block_mask_count(const int64_t* x, int64_t ld, int lo, int block, int 
 int mmada_text_transfer(int64_t* x, int64_t ld, int lo, int block, const int64_t* x0, const double* conf,
                         const double* conf_override, const int32_t* cnt, int steps, int step, int B,
                         int64_t mask_id, uint8_t* transfer_out, void* stream);
+
+/* ---- MAGVIT-v2 token -> pixel path ------------------------------------------------------------
+ * Activations are NHWC (channels contiguous).  conv: implicit GEMM on tcgen05, zero padding by TMA
+ * out-of-bounds fill; in bf16 [B,H,W,C_in] (C_in % 64 == 0), weight bf16 [C_out][taps][C_in] (taps 9 = 3x3
+ * pad 1, or 1), bias fp32 [C_out]; epilogue one of MMADA_EPI_BIAS_{BF16,F32,RESID_F32} (resid fp32
+ * [B,H,W,C_out]).  Replaces torch.nn.Conv2d in models/modeling_magvitv2.py:309-362 and
+ * models/common_modules.py (ResnetBlock, Upsample, AttnBlock).                                       */
+int mmada_conv_nhwc_bf16(const void* in, const void* weight, const float* bias, void* out, const void* resid,
+                         int B, int H, int W, int C_in, int C_out, int taps, int epilogue, void* stream);
+/* LFQuantizer (models/modeling_magvitv2.py:186-221).  lfq_decode: indices [total] -> bf16 NHWC
+ * [total,64], channels 0..12 = post_quant_conv (1x1, weight fp32 [13,13], bias [13]) applied to the
+ * -1/+1 bits (MSB first), channels 13..63 zero.  indices_to_bits: [B,N] -> fp32 [B,13,N] (NCHW).
+ * bits_to_indices: fp32 [B,13,N] -> int64 [B,N].                                                    */
+int mmada_lfq_decode_nhwc(const int64_t* indices, const float* pq_weight, const float* pq_bias, void* out_bf16,
+                          int total_tokens, void* stream);
+int mmada_lfq_indices_to_bits(const int64_t* indices, float* out_nchw, int B, int N, void* stream);
+int mmada_lfq_bits_to_indices(const float* z_nchw, int64_t* out, int B, int N, void* stream);
+/* GroupNorm(32 groups) over fp32 NHWC [B,P,C]: stats accumulates (sum, sum of squares) per (b, group)
+ * into sums fp64 [B,32,2] (zeroed by the call); apply writes bf16 (x-mean)*rstd*gamma+beta, optional
+ * swish.  models/common_modules.py:16-24.                                                           */
+int mmada_groupnorm_stats(const float* x, double* sums, int B, int P, int C, void* stream);
+int mmada_groupnorm_apply_bf16(const float* x, const double* sums, const float* gamma, const float* beta,
+                               void* out_bf16, int B, int P, int C, float eps, int swish, void* stream);
+int mmada_upsample2x_nhwc_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream);
+int mmada_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
+int mmada_softmax_rows_bf16(const float* x, void* out_bf16, int R, int n, float scale, void* stream);
+int mmada_nhwc_to_nchw_f32(const float* x, float* out, int B, int P, int C, void* stream);
+int mmada_image_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

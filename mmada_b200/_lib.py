@@ -20,7 +20,7 @@ _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "mmada_abi_version": [],
     "mmada_device_arch": [],
-    "mmada_gemm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _p],
+    "mmada_gemm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _p],
     "mmada_embed_f32": [_p, _p, _p, _i, _i, _i64, _p],
     "mmada_rmsnorm_bf16": [_p, _p, _p, _p, _i, _i, _f, _p],
     "mmada_rope_inplace_bf16": [_p, _i64, _p, _p, _i, _i, _i, _i, _p],
@@ -31,6 +31,17 @@ SIGNATURES = {
     "mmada_text_sample_rows": [_p, _p, _f, _p, C.c_uint64, _f, _i, _i, _p, _p, _p],
     "mmada_block_mask_count": [_p, _i64, _i, _i, _i, _i64, _p, _p],
     "mmada_text_transfer": [_p, _i64, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i64, _p, _p],
+    "mmada_conv_nhwc_bf16": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mmada_lfq_decode_nhwc": [_p, _p, _p, _p, _i, _p],
+    "mmada_lfq_indices_to_bits": [_p, _p, _i, _i, _p],
+    "mmada_lfq_bits_to_indices": [_p, _p, _i, _i, _p],
+    "mmada_groupnorm_stats": [_p, _p, _i, _i, _i, _p],
+    "mmada_groupnorm_apply_bf16": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _i, _p],
+    "mmada_upsample2x_nhwc_bf16": [_p, _p, _i, _i, _i, _i, _p],
+    "mmada_cast_f32_bf16": [_p, _p, _i64, _p],
+    "mmada_softmax_rows_bf16": [_p, _p, _i, _i, _f, _p],
+    "mmada_nhwc_to_nchw_f32": [_p, _p, _i, _i, _i, _p],
+    "mmada_image_to_uint8": [_p, _p, _i64, _p],
 }
 
 

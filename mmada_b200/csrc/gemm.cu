@@ -1,22 +1,26 @@
-// tcgen05 / TMEM / TMA GEMM for the LLaDA block projections and the restricted lm_head.
+// tcgen05 / TMEM / TMA GEMM for the LLaDA block projections, the restricted lm_head and (as an
+// implicit GEMM) the 3x3 / 1x1 convolutions of the MAGVIT-v2 decoder.
 //
-//   D[M,N] = A[M,K] . B[N,K]^T      A, B bf16 row-major (K contiguous), fp32 accumulation in TMEM
+//   D[M,N] = A[M,K] . B[N,K]^T      A, B bf16 (K contiguous), fp32 accumulation in TMEM
 //
 // replaces the nn.Linear calls of the reference's LLaDALlamaBlock
 // (/root/reference/models/modeling_llada.py:901-903 q/k/v_proj, :724 attn_out, :924 ff_proj/up_proj,
-//  :930 ff_out, :1362 transformer.ff_out), each a cuBLAS GEMM there.
+//  :930 ff_out, :1362 transformer.ff_out), each a cuBLAS GEMM there, and the cuDNN convolutions of
+// VQGANDecoder (/root/reference/models/modeling_magvitv2.py:365-399, models/common_modules.py).
 //
 // Structure (one persistent CTA, or CTA pair, per SM):
 //   warp 0      TMA producer: A and B k-blocks (64 columns = one 128-byte swizzle row) into a ring of
-//               shared-memory stages, signalled through mbarriers
-//   warp 1      allocates TMEM; one lane issues tcgen05.mma (UMMA 128x256x16, or 256x256x16 with
-//               cta_group::2) into one of two 256-column accumulator stages; tcgen05.commit releases
+//               shared-memory stages, signalled through mbarriers.  In convolution mode the A tile is
+//               a 4-D box (64 channels x BW x BH pixels of one image, NHWC) fetched at the tap's
+//               offset; out-of-image coordinates are zero-filled by the TMA unit = zero padding.
+//   warp 1      allocates TMEM; one elected lane issues tcgen05.mma (UMMA 128xBNx16, or 256xBNx16 with
+//               cta_group::2) into one of two BN-column accumulator stages; tcgen05.commit releases
 //               smem stages and publishes finished accumulators
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (one warp per 32-lane quarter), apply the fused
 //               epilogue, store to global; overlaps with the next tile's MMAs
-//
-// Epilogues: bf16 store | fp32 store | fp32 residual add (x + acc) | SwiGLU silu(gate)*up with gate and
-// up interleaved in 128-row blocks of B | bf16 store with per-column bias.
+// The producer and MMA warps run their loops with all 32 lanes (addresses stay warp-uniform) and
+// elect one lane only around the TMA / MMA instructions: a single diverged lane executing the loop
+// bookkeeping was measured to cap the tensor pipe at ~36 %.
 #include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mmada_b200.h"
@@ -25,26 +29,28 @@ namespace mmada {
 
 constexpr int BK = 64;          // k-block: 64 bf16 = 128 bytes = one swizzle row
 constexpr int BM = 128;         // A rows per CTA
-constexpr int BN = 256;         // accumulator columns per tile
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int GROUP_M = 8;      // rasterisation: tiles walk GROUP_M m-tiles before the next n-tile
 
 struct GemmParams {
     void* out;
-    const void* aux;     // residual (fp32, ld = ldo) or bias (fp32[N])
+    const void* aux;     // residual (fp32, ld = ldo)
+    const float* bias;   // fp32 [N]
     int64_t ldo;
     int M, N, K;
     int num_m_tiles, num_n_tiles;
+    // convolution mode (A = NHWC activations [B,H,W,C], K = taps * C)
+    int conv_H, conv_W, conv_C, conv_taps;   // taps = 9 (3x3, pad 1) or 1
 };
 
-template <int CG>
+template <int CG, int BN>
 struct GemmCfg {
     static constexpr int LOAD_N = BN / CG;                     // B rows loaded per CTA
     static constexpr int A_BYTES = BM * BK * 2;                // 16 KiB
-    static constexpr int B_BYTES = LOAD_N * BK * 2;            // 32 / 16 KiB
+    static constexpr int B_BYTES = LOAD_N * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = CG == 1 ? 4 : 6;
+    static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -60,36 +66,34 @@ __device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+__host__ __device__ constexpr bool epi_has_bias(int e) { return e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_BIAS_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
+__host__ __device__ constexpr bool epi_has_resid(int e) { return e == MMADA_EPI_RESID_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
+__host__ __device__ constexpr bool epi_out_bf16(int e) { return e == MMADA_EPI_BF16 || e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_SWIGLU_BF16; }
+
 // one 32-column chunk of one accumulator row
 template <int EPI>
 __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int col0, const uint32_t (&v)[32]) {
     if (row >= p.M) return;
     const int ncols = min(32, p.N - col0);
     if (ncols <= 0) return;
-    if constexpr (EPI == MMADA_EPI_BF16 || EPI == MMADA_EPI_BIAS_BF16) {
+    float f[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        f[t] = __uint_as_float(v[t]);
+        if constexpr (epi_has_bias(EPI)) f[t] += (t < ncols) ? __ldg(p.bias + col0 + t) : 0.f;
+    }
+    if constexpr (epi_out_bf16(EPI)) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldo + col0;
-        const float* bias = reinterpret_cast<const float*>(p.aux);
         if (ncols == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float f[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    f[t] = __uint_as_float(v[8 * j + t]);
-                    if constexpr (EPI == MMADA_EPI_BIAS_BF16) f[t] += __ldg(bias + col0 + 8 * j + t);
-                }
-                uint4 w = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                     pack_bf16(f[6], f[7]));
-                *reinterpret_cast<uint4*>(o + 8 * j) = w;
-            }
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(o + 8 * j) =
+                    make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
         } else {
 #pragma unroll
             for (int t = 0; t < 32; ++t)
-                if (t < ncols) {
-                    float f = __uint_as_float(v[t]);
-                    if constexpr (EPI == MMADA_EPI_BIAS_BF16) f += __ldg(bias + col0 + t);
-                    o[t] = __float2bfloat16_rn(f);
-                }
+                if (t < ncols) o[t] = __float2bfloat16_rn(f[t]);
         }
     } else {  // fp32 store, optional residual
         float* o = reinterpret_cast<float*>(p.out) + (int64_t)row * p.ldo + col0;
@@ -97,10 +101,9 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int co
         if (ncols == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                if constexpr (EPI == MMADA_EPI_RESID_F32) {
-                    float4 b = *reinterpret_cast<const float4*>(r + 4 * j);
+                float4 a = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                if constexpr (epi_has_resid(EPI)) {
+                    const float4 b = *reinterpret_cast<const float4*>(r + 4 * j);
                     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
                 }
                 *reinterpret_cast<float4*>(o + 4 * j) = a;
@@ -109,18 +112,18 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int co
 #pragma unroll
             for (int t = 0; t < 32; ++t)
                 if (t < ncols) {
-                    float f = __uint_as_float(v[t]);
-                    if constexpr (EPI == MMADA_EPI_RESID_F32) f += r[t];
-                    o[t] = f;
+                    float x = f[t];
+                    if constexpr (epi_has_resid(EPI)) x += r[t];
+                    o[t] = x;
                 }
         }
     }
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int BN, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
-    using Cfg = GemmCfg<CG>;
+    using Cfg = GemmCfg<CG, BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
@@ -167,7 +170,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // The whole warp runs the loop (addresses stay in uniform registers); one elected lane issues.
         const uint32_t full0 = CG == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);   // leader's barriers
         int stage = 0;
         uint32_t phase = 0;
@@ -176,23 +178,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
             const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
             const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
+            // convolution: the 128 rows are 128 consecutive NHWC pixels = a BW x BH box of one image
+            int cb = 0, cy = 0, cx = 0, kpc = 1;
+            if constexpr (CONV) {
+                const int hw = p.conv_H * p.conv_W;
+                cb = m0 / hw;
+                const int rem = m0 - cb * hw;
+                cy = rem / p.conv_W;
+                cx = rem - cy * p.conv_W;
+                kpc = p.conv_C / BK;          // k-blocks per tap
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1, 1);
                 const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t sb = sa + Cfg::A_BYTES;
                 if (elect_one()) {
-                    if constexpr (CG == 1) {
-                        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                        tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
-                        tma_load_2d(sb, &map_b, full_bar(stage), kb * BK, n0);
+                    const uint32_t fb = CG == 2 ? full0 + 8 * stage : full_bar(stage);
+                    if (CG == 1 || leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * CG);
+                    // (2-CTA: both CTAs' bytes are accounted on the leader's barrier; the peer's complete_tx may
+                    //  precede the leader's expect_tx within the phase — transiently negative tx-count)
+                    if constexpr (CONV) {
+                        const int tap = kb / kpc, kc = kb - tap * kpc;
+                        const int dy = p.conv_taps == 9 ? tap / 3 - 1 : 0, dx = p.conv_taps == 9 ? tap % 3 - 1 : 0;
+                        if constexpr (CG == 1) tma_load_4d(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb);
+                        else tma_load_4d_2sm(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb);
                     } else {
-                        // both CTAs' bytes are accounted on the leader's barrier; the peer's complete_tx may
-                        // precede the leader's expect_tx within the phase (transiently negative tx-count)
-                        const uint32_t fb = full0 + 8 * stage;
-                        if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES * 2);
-                        tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0);
-                        tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0);
+                        if constexpr (CG == 1) tma_load_2d(sa, &map_a, fb, kb * BK, m0);
+                        else tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0);
                     }
+                    if constexpr (CG == 1) tma_load_2d(sb, &map_b, fb, kb * BK, n0);
+                    else tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -250,10 +265,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
             if constexpr (EPI == MMADA_EPI_SWIGLU_BF16) {
-                // columns [0,128) = gate, [128,256) = up for output columns nt*128 + [0,128)
+                // columns [0,BN/2) = gate, [BN/2,BN) = up for output columns nt*BN/2 + [0,BN/2)
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldo + nt * (BN / 2);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < BN / 64; ++c) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(t_addr + c * 32, g);
                     tmem_ld_32x32b_x32(t_addr + BN / 2 + c * 32, u);
@@ -299,10 +314,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int BN, bool CONV>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<CG>;
-    auto kern = gemm_kernel<CG, EPI>;
+    using Cfg = GemmCfg<CG, BN>;
+    auto kern = gemm_kernel<CG, EPI, BN, CONV>;
     static bool configured = false;
     if (!configured) {
         MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -327,14 +342,37 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
     return kOk;
 }
 
+// plain GEMM: every epilogue at BN = 256 for both CTA-group sizes
 template <int CG>
-static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+static int dispatch_gemm256(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
     switch (epi) {
-        case MMADA_EPI_BF16: return launch_gemm<CG, MMADA_EPI_BF16>(ma, mb, p, s);
-        case MMADA_EPI_F32: return launch_gemm<CG, MMADA_EPI_F32>(ma, mb, p, s);
-        case MMADA_EPI_RESID_F32: return launch_gemm<CG, MMADA_EPI_RESID_F32>(ma, mb, p, s);
-        case MMADA_EPI_SWIGLU_BF16: return launch_gemm<CG, MMADA_EPI_SWIGLU_BF16>(ma, mb, p, s);
-        case MMADA_EPI_BIAS_BF16: return launch_gemm<CG, MMADA_EPI_BIAS_BF16>(ma, mb, p, s);
+        case MMADA_EPI_BF16: return launch_gemm<CG, MMADA_EPI_BF16, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_F32: return launch_gemm<CG, MMADA_EPI_F32, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_RESID_F32: return launch_gemm<CG, MMADA_EPI_RESID_F32, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_SWIGLU_BF16: return launch_gemm<CG, MMADA_EPI_SWIGLU_BF16, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_BF16: return launch_gemm<CG, MMADA_EPI_BIAS_BF16, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_F32: return launch_gemm<CG, MMADA_EPI_BIAS_F32, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_RESID_F32: return launch_gemm<CG, MMADA_EPI_BIAS_RESID_F32, 256, false>(ma, mb, p, s);
+    }
+    return kBadArgument;
+}
+// narrow outputs (N <= 128): BN = 128, pairs only
+template <bool CONV>
+static int dispatch_narrow(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+    switch (epi) {
+        case MMADA_EPI_BF16: return launch_gemm<2, MMADA_EPI_BF16, 128, CONV>(ma, mb, p, s);
+        case MMADA_EPI_F32: return launch_gemm<2, MMADA_EPI_F32, 128, CONV>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_BF16: return launch_gemm<2, MMADA_EPI_BIAS_BF16, 128, CONV>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_F32: return launch_gemm<2, MMADA_EPI_BIAS_F32, 128, CONV>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_RESID_F32: return launch_gemm<2, MMADA_EPI_BIAS_RESID_F32, 128, CONV>(ma, mb, p, s);
+    }
+    return kBadArgument;
+}
+static int dispatch_conv256(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t s) {
+    switch (epi) {
+        case MMADA_EPI_BIAS_BF16: return launch_gemm<2, MMADA_EPI_BIAS_BF16, 256, true>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_F32: return launch_gemm<2, MMADA_EPI_BIAS_F32, 256, true>(ma, mb, p, s);
+        case MMADA_EPI_BIAS_RESID_F32: return launch_gemm<2, MMADA_EPI_BIAS_RESID_F32, 256, true>(ma, mb, p, s);
     }
     return kBadArgument;
 }
@@ -344,25 +382,61 @@ static int dispatch_epi(int epi, const CUtensorMap& ma, const CUtensorMap& mb, c
 using namespace mmada;
 
 extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
-                               const void* aux, int M, int N, int K, int epilogue, int cta_group, void* stream) {
+                               const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
+                               void* stream) {
     if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return kBadArgument;
     if ((lda % 8) || (ldb % 8) || (K % 8)) return kUnsupportedShape;        // 16-byte global strides for TMA
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return kBadArgument;
-    if (epilogue == MMADA_EPI_SWIGLU_BF16 && (N % BN)) return kUnsupportedShape;
-    if ((epilogue == MMADA_EPI_RESID_F32 || epilogue == MMADA_EPI_BIAS_BF16) && !aux) return kBadArgument;
+    if (epilogue < 0 || epilogue > MMADA_EPI_BIAS_RESID_F32) return kBadArgument;
+    if (epilogue == MMADA_EPI_SWIGLU_BF16 && (N % 256)) return kUnsupportedShape;
+    if (epi_has_resid(epilogue) && !aux) return kBadArgument;
+    if (epi_has_bias(epilogue) && !bias) return kBadArgument;
     if (cta_group != 1 && cta_group != 2) return kBadArgument;
+    const bool narrow = N <= 128 && cta_group == 2 && epilogue != MMADA_EPI_SWIGLU_BF16 && epilogue != MMADA_EPI_RESID_F32;
+    const int bn = narrow ? 128 : 256;
     CUtensorMap ma, mb;
     int st = make_tmap_bf16_2d(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
     if (st) return st;
-    st = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(BN / cta_group));
+    st = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(bn / cta_group));
     if (st) return st;
-    GemmParams p;
-    p.out = out;
-    p.aux = aux;
-    p.ldo = ldo;
+    GemmParams p = {};
+    p.out = out; p.aux = aux; p.bias = bias; p.ldo = ldo;
     p.M = M; p.N = N; p.K = K;
     p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
-    p.num_n_tiles = (N + BN - 1) / BN;
+    p.num_n_tiles = (N + bn - 1) / bn;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return cta_group == 1 ? dispatch_epi<1>(epilogue, ma, mb, p, s) : dispatch_epi<2>(epilogue, ma, mb, p, s);
+    if (narrow) return dispatch_narrow<false>(epilogue, ma, mb, p, s);
+    return cta_group == 1 ? dispatch_gemm256<1>(epilogue, ma, mb, p, s) : dispatch_gemm256<2>(epilogue, ma, mb, p, s);
+}
+
+// NHWC convolution as an implicit GEMM: out[b,y,x,co] = bias[co] + sum_{tap,c} in[b,y+dy,x+dx,c] * w[co,tap,c] (+ resid)
+extern "C" int mmada_conv_nhwc_bf16(const void* in, const void* weight, const float* bias, void* out, const void* resid,
+                                    int B, int H, int W, int C_in, int C_out, int taps, int epilogue, void* stream) {
+    if (!in || !weight || !bias || !out || B <= 0 || H <= 0 || W <= 0) return kBadArgument;
+    if (taps != 9 && taps != 1) return kBadArgument;
+    if (C_in % 64) return kUnsupportedShape;                       // whole k-blocks per tap
+    const int bw = W >= 128 ? 128 : W;
+    if (128 % bw || W % bw) return kUnsupportedShape;
+    const int bh = 128 / bw;
+    if (H % bh) return kUnsupportedShape;
+    if (!epi_has_bias(epilogue)) return kBadArgument;
+    if (epi_has_resid(epilogue) && !resid) return kBadArgument;
+    CUtensorMap ma, mb;
+    const uint64_t dims[4] = {(uint64_t)C_in, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C_in * 2, (uint64_t)W * C_in * 2, (uint64_t)H * W * C_in * 2};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    int st = make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in, dims, strides, box);
+    if (st) return st;
+    const int K = taps * C_in;
+    const int bn = C_out <= 128 ? 128 : 256;
+    st = make_tmap_bf16_2d(&mb, weight, (uint64_t)C_out, (uint64_t)K, (uint64_t)K, (uint32_t)(bn / 2));
+    if (st) return st;
+    GemmParams p = {};
+    p.out = out; p.aux = resid; p.bias = bias; p.ldo = C_out;
+    p.M = B * H * W; p.N = C_out; p.K = K;
+    p.num_m_tiles = (p.M + 255) / 256;
+    p.num_n_tiles = (C_out + bn - 1) / bn;
+    p.conv_H = H; p.conv_W = W; p.conv_C = C_in; p.conv_taps = taps;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return bn == 128 ? dispatch_narrow<true>(epilogue, ma, mb, p, s) : dispatch_conv256(epilogue, ma, mb, p, s);
 }

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_BF16, EPI_BIAS_BF16 = range(5)
+EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_BF16, EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_RESID_F32 = range(7)
 
 
 #: when set to a list, every GEMM launch appends (start_event, end_event, M, N, K, epilogue) — used by
@@ -33,7 +33,7 @@ def _chk(t: torch.Tensor, dtype, name: str):
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Optional[torch.Tensor] = None,
-         aux: Optional[torch.Tensor] = None, cta_group: int = 2) -> torch.Tensor:
+         aux: Optional[torch.Tensor] = None, cta_group: int = 2, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a[M,K] @ w[N,K]^T); a, w bf16 with contiguous K."""
     _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w")
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
@@ -42,17 +42,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Option
     N = w.shape[0]
     n_out = N // 2 if epilogue == EPI_SWIGLU_BF16 else N
     if out is None:
-        dt = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32) else torch.bfloat16
+        dt = torch.float32 if epilogue in (EPI_F32, EPI_RESID_F32, EPI_BIAS_F32, EPI_BIAS_RESID_F32) else torch.bfloat16
         out = torch.empty((M, n_out), dtype=dt, device=a.device)
     assert out.shape == (M, n_out) and out.stride(1) == 1
-    if epilogue == EPI_RESID_F32:
+    if epilogue in (EPI_RESID_F32, EPI_BIAS_RESID_F32):
         assert aux is not None and aux.dtype == torch.float32 and aux.stride(0) == out.stride(0)
+    if epilogue in (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_RESID_F32):
+        assert bias is not None and bias.dtype == torch.float32 and bias.numel() == N
     ev = GEMM_EVENTS
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.call("mmada_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
-              _ptr(aux), M, N, K, epilogue, cta_group, _stream())
+              _ptr(aux), _ptr(bias), M, N, K, epilogue, cta_group, _stream())
     if ev is not None:
         e1.record()
         ev.append((e0, e1, M, N, K, epilogue))
@@ -191,3 +193,97 @@ def text_transfer(x: torch.Tensor, lo: int, block: int, x0: torch.Tensor, conf: 
     _lib.call("mmada_text_transfer", x.data_ptr(), x.stride(0), lo, block, x0.data_ptr(), _ptr(conf), _ptr(conf_override),
               cnt.data_ptr(), steps, step, B, mask_id, _ptr(tr), _stream())
     return tr.bool() if want_transfer else None
+
+
+# ---- MAGVIT-v2 decoder ops (NHWC) ---------------------------------------------------------------
+def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, taps: int, epilogue: int = EPI_BIAS_F32,
+              resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [B,H,W,Cin]; weight bf16 [Cout, taps*Cin]; bias fp32 [Cout] -> [B,H,W,Cout]."""
+    _chk(x, torch.bfloat16, "x"); _chk(weight, torch.bfloat16, "weight"); _chk(bias, torch.float32, "bias")
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    assert x.is_contiguous() and weight.is_contiguous() and weight.shape[1] == taps * Cin
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16 if epilogue == EPI_BIAS_BF16 else torch.float32)
+    if resid is not None:
+        _chk(resid, torch.float32, "resid")
+        assert resid.is_contiguous() and resid.shape == out.shape
+    _lib.call("mmada_conv_nhwc_bf16", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(resid), B, H, W,
+              Cin, Cout, taps, epilogue, _stream())
+    return out
+
+
+def lfq_decode_nhwc(indices: torch.Tensor, pq_weight: torch.Tensor, pq_bias: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    _chk(indices, torch.int64, "indices")
+    B = indices.shape[0]
+    out = torch.empty((B, h, w, 64), device=indices.device, dtype=torch.bfloat16)
+    _lib.call("mmada_lfq_decode_nhwc", indices.contiguous().data_ptr(), pq_weight.data_ptr(), pq_bias.data_ptr(),
+              out.data_ptr(), indices.numel(), _stream())
+    return out
+
+
+def lfq_indices_to_bits(indices: torch.Tensor) -> torch.Tensor:
+    _chk(indices, torch.int64, "indices")
+    B, N = indices.shape
+    out = torch.empty((B, 13, N), device=indices.device, dtype=torch.float32)
+    _lib.call("mmada_lfq_indices_to_bits", indices.contiguous().data_ptr(), out.data_ptr(), B, N, _stream())
+    return out
+
+
+def lfq_bits_to_indices(z: torch.Tensor) -> torch.Tensor:
+    _chk(z, torch.float32, "z")
+    B, N = z.shape[0], z[0, 0].numel()
+    out = torch.empty((B, N), device=z.device, dtype=torch.int64)
+    _lib.call("mmada_lfq_bits_to_indices", z.contiguous().data_ptr(), out.data_ptr(), B, N, _stream())
+    return out
+
+
+def groupnorm_swish(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, sums: torch.Tensor, swish: bool = True,
+                    eps: float = 1e-6) -> torch.Tensor:
+    """x fp32 NHWC [B,H,W,C] -> bf16 NHWC; sums: fp64 scratch [B,32,2]."""
+    _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and sums.dtype == torch.float64 and sums.numel() >= B * 64
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_groupnorm_stats", x.data_ptr(), sums.data_ptr(), B, H * W, C, _stream())
+    _lib.call("mmada_groupnorm_apply_bf16", x.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+              B, H * W, C, float(eps), 1 if swish else 0, _stream())
+    return out
+
+
+def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_upsample2x_nhwc_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_cast_f32_bf16", x.contiguous().data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def softmax_rows_bf16(x: torch.Tensor, scale: float) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    R, n = x.shape
+    out = torch.empty((R, n), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_softmax_rows_bf16", x.contiguous().data_ptr(), out.data_ptr(), R, n, float(scale), _stream())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("mmada_nhwc_to_nchw_f32", x.contiguous().data_ptr(), out.data_ptr(), B, H * W, C, _stream())
+    return out
+
+
+def image_to_uint8(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    _lib.call("mmada_image_to_uint8", x.contiguous().data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
