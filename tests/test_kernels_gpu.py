@@ -39,7 +39,7 @@ def test_gemm_residual_swiglu_bias(cta_group):
     wo = (torch.randn(512, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
     x = torch.randn(M, 512, device="cuda", generator=g)
     ref = x + a.float() @ wo.float().t()
-    out = ops.gemm(a, wo, ops.EPI_RESID_F32, out=x.clone(), aux=None if False else x, cta_group=cta_group)
+    out = ops.gemm(a, wo, ops.EPI_RESID_F32, out=x.clone(), aux=x, cta_group=cta_group)
     assert _rel(out, ref) < 1e-5
     xi = x.clone()                                    # in place: out aliases aux
     ops.gemm(a, wo, ops.EPI_RESID_F32, out=xi, aux=xi, cta_group=cta_group)
@@ -54,8 +54,14 @@ def test_gemm_residual_swiglu_bias(cta_group):
     assert h.shape == (M, F)
     assert _rel(h.float(), ref) < 6e-3
     bias = torch.randn(512, device="cuda", generator=g)
-    ob = ops.gemm(a, wo, ops.EPI_BIAS_BF16, aux=bias, cta_group=cta_group)
+    ob = ops.gemm(a, wo, ops.EPI_BIAS_BF16, bias=bias, cta_group=cta_group)
     assert _rel(ob.float(), a.float() @ wo.float().t() + bias) < 5e-3
+    x2 = torch.randn(M, 512, device="cuda", generator=g)
+    o3 = ops.gemm(a, wo, ops.EPI_BIAS_RESID_F32, aux=x2, bias=bias, cta_group=cta_group)
+    assert _rel(o3, a.float() @ wo.float().t() + bias + x2) < 1e-5
+    wn = wo[:96].contiguous()                      # narrow output (BN = 128 path for pairs)
+    o4 = ops.gemm(a, wn, ops.EPI_BIAS_F32, bias=bias[:96].contiguous(), cta_group=cta_group)
+    assert _rel(o4, a.float() @ wn.float().t() + bias[:96]) < 1e-5
 
 
 @pytest.mark.parametrize("d", [256, 512, 1024, 4096, 384])

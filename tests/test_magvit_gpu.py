@@ -96,7 +96,7 @@ def test_decode_code_vs_reference_golden(golden):
     rms = float((mine - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
     print(f"decode_code 16x16: max|d|/max|ref| = {err:.3e}, rel-rms = {rms:.3e}")
     # bf16 conv operands (fp32 accumulate, fp32 trunk) through 60 conv layers vs the fp32 reference
-    assert err < 3e-2 and rms < 1e-2
+    assert err < 3e-2 and rms < 2e-2
     u8 = vq.decode_code_uint8(idx)
     exp = (torch.clamp((pix + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).cpu().numpy().astype(np.uint8)
     assert np.array_equal(u8.cpu().numpy(), exp)
