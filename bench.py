@@ -184,7 +184,8 @@ def run_own(args):
     cond_h = cond_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
     unc_h = unc_h[rank * B:(rank + 1) * B].contiguous().pin_memory()
     L = cond_h.shape[1]
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    from mmada_b200.dist import gather_rows, prompt_seed
+    gen = [torch.Generator(device=dev).manual_seed(prompt_seed(1234, rank * B + i)) for i in range(B)]
     vq = None
     try:
         from mmada_b200.modeling_magvitv2 import MAGVITv2
@@ -257,8 +258,7 @@ def run_own(args):
         else:
             res = codes
         if world > 1:
-            gathered = [torch.empty_like(res) for _ in range(world)]
-            dist.all_gather(gathered, res)
+            res_all = gather_rows(res, B * world)          # the path's only collective (NCCL all-gather)
         out_h.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     t_e1.record()

@@ -76,13 +76,16 @@ int mmada_attention_bf16(const void* q, const void* k, const void* v, int64_t ld
  *   known_ids int64 [B,N] in/out (code id, or mask_id where unknown);
  *   input_ids int64 [B, ld_ids] in/out, image tokens at columns [img_off, img_off+N) (may be NULL);
  *   sampled_out int64 [B,N]; sel_out fp32 [B,N]; masking_out uint8 [B,N] (may be NULL);
+ *   raw_out int64 [B,N] (may be NULL): raw argmax at every position, known ones included;
+ *   no_remask != 0: commit the merged tokens without re-masking — both for
+ *   t2m_generate (models/modelling_ours.py:634-682, Appendix A Q15);
  *   tickets int32 [B], zero on entry and left zero.                                            */
 int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, const float* q_noise,
                           const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
                           int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
-                          int32_t* tickets, int B, int N, int C, float one_plus_g, float g,
-                          float mask_len_raw, float temperature, int64_t mask_id, int64_t text_vocab,
-                          void* stream);
+                          int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
+                          float one_plus_g, float g, float mask_len_raw, float temperature,
+                          int64_t mask_id, int64_t text_vocab, void* stream);
 /* masking[b,n] = conf[b,n] < sort(conf[b])[mask_len[b]], conf = log(max(p,1e-20)) + T*gumbel(u).
  * Replaces mask_by_random_topk, models/sampling.py:31-36.                                      */
 int mmada_mask_by_random_topk(const float* probs, const float* u_noise, const int64_t* mask_len,

@@ -36,6 +36,8 @@ struct T2ISampleParams {
     int64_t* sampled_out;   // [B, N]
     float* sel_out;         // [B, N]    selected probs (finfo.max at known positions)
     uint8_t* masking_out;   // [B, N]    optional
+    int64_t* raw_out;       // [B, N]    optional: the raw argmax(p/q) at EVERY position (disables the known-row skip)
+    int no_remask;          // 1: commit the merged tokens and skip the re-masking (t2m_generate's last step)
     int32_t* tickets;       // [B]       zero on entry, zero on exit
     int64_t ld_ids;
     int64_t img_off;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(THREADS) t2i_sample_kernel(const T2ISamplePara
     constexpr int NW = THREADS / 32;
     const int64_t known = p.known[row];
 
-    if (known != p.mask_id) {
+    if (known != p.mask_id && p.raw_out == nullptr) {
         if (tid == 0) {
             p.sampled_out[row] = known;
             p.sel_out[row] = FLT_MAX;
@@ -229,10 +231,22 @@ __global__ void __launch_bounds__(THREADS) t2i_sample_kernel(const T2ISamplePara
                 if (ob > best || (ob == best && oi < best_i)) { best = ob; best_p = op; best_i = oi; }
             }
             if (lane == 0) {
-                p.sampled_out[row] = best_i == 0x7fffffff ? 0 : best_i;
-                p.sel_out[row] = best_p;
+                const int64_t tok = best_i == 0x7fffffff ? 0 : best_i;
+                if (p.raw_out) p.raw_out[row] = tok;
+                p.sampled_out[row] = known != p.mask_id ? known : tok;
+                p.sel_out[row] = known != p.mask_id ? FLT_MAX : best_p;
             }
         }
+    }
+    if (p.no_remask) {
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t tok = p.sampled_out[row];
+            if (p.input_ids) p.input_ids[(int64_t)b * p.ld_ids + p.img_off + (row - b * p.N)] = tok + p.text_vocab;
+            p.known[row] = tok;
+            if (p.masking_out) p.masking_out[row] = 0;
+        }
+        return;
     }
     // ---- ticket: the last CTA of batch row b re-masks it
     __syncthreads();
@@ -280,9 +294,9 @@ using namespace mmada;
 extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, const float* q_noise,
                                      const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
                                      int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
-                                     int32_t* tickets, int B, int N, int C, float one_plus_g, float g,
-                                     float mask_len_raw, float temperature, int64_t mask_id, int64_t text_vocab,
-                                     void* stream) {
+                                     int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
+                                     float one_plus_g, float g, float mask_len_raw, float temperature,
+                                     int64_t mask_id, int64_t text_vocab, void* stream) {
     if (!cond_logits || !q_noise || !u_noise || !known_ids || !sampled_out || !sel_out || !tickets) return kBadArgument;
     if (B <= 0 || N <= 0 || N > MAX_TOKENS) return kUnsupportedShape;
     if ((reinterpret_cast<uintptr_t>(cond_logits) | reinterpret_cast<uintptr_t>(uncond_logits) |
@@ -291,7 +305,7 @@ extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* unco
     T2ISampleParams p;
     p.cond = cond_logits; p.uncond = uncond_logits; p.q = q_noise; p.u = u_noise;
     p.known = known_ids; p.input_ids = input_ids; p.sampled_out = sampled_out; p.sel_out = sel_out;
-    p.masking_out = masking_out; p.tickets = tickets; p.ld_ids = ld_ids; p.img_off = img_off;
+    p.masking_out = masking_out; p.raw_out = raw_out; p.no_remask = no_remask; p.tickets = tickets; p.ld_ids = ld_ids; p.img_off = img_off;
     p.mask_id = mask_id; p.text_vocab = text_vocab; p.B = B; p.N = N; p.C = C;
     p.one_plus_g = one_plus_g; p.g = g; p.mask_len_raw = mask_len_raw; p.temperature = temperature;
     cudaStream_t s = (cudaStream_t)stream;

@@ -31,29 +31,10 @@ class MMadaConfig(LLaDAConfig):
 
 class MMadaModelLM(LLaDAModelLM):
     # ------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def t2i_generate(
-            self,
-            input_ids: torch.LongTensor = None,
-            uncond_input_ids: torch.LongTensor = None,
-            attention_mask=None,
-            uncond_attention_mask=None,
-            temperature=1.0,
-            timesteps=18,
-            guidance_scale=0,
-            noise_schedule=cosine_schedule,
-            generator: torch.Generator = None,
-            config=None,
-            seq_len=1024,
-            mask_token_id=126336,
-            resolution=512,
-            codebook_size=8192,
-            **kwargs,
-    ):
-        """MaskGIT-style parallel decoding with classifier-free guidance; returns (B, seq_len) int64
-        code ids and leaves ``input_ids`` mutated like the reference (:206).  Extra kwargs:
-        ``uni_prompting`` (only ``len(uni_prompting.text_tokenizer)`` is read, :149) and, for parity
-        tests, ``noise`` = per-step list of (q [B*N, C] ~ Exp(1), u [B, N] ~ U(0,1))."""
+    def _t2i_steps(self, input_ids, uncond_input_ids, temperature, timesteps, guidance_scale, noise_schedule, generator,
+                   seq_len, mask_token_id, resolution, codebook_size, kwargs):
+        """The denoising loop of t2i_generate as a Python generator: yields (step, sampled_ids) after
+        every step (sampled_ids = the step's predictions merged with the already-known tokens)."""
         uni_prompting = kwargs.get("uni_prompting", None)
         text_vocab = len(uni_prompting.text_tokenizer)
         noise = kwargs.get("noise", None)
@@ -77,7 +58,6 @@ class MMadaModelLM(LLaDAModelLM):
         rows = (torch.arange(R, device=dev, dtype=torch.int32)[:, None] * L + img_off
                 + torch.arange(N, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
         tickets = torch.zeros(B, dtype=torch.int32, device=dev)
-        sampled = None
         for step in range(timesteps):
             if stop_after is not None and step >= stop_after:
                 break
@@ -90,6 +70,13 @@ class MMadaModelLM(LLaDAModelLM):
             if noise is not None:
                 q, u = noise[step]
                 q, u = q.to(dev), u.to(dev)
+            elif isinstance(generator, (list, tuple)):
+                # one generator per prompt: the noise of a prompt does not depend on batch composition / world size
+                q = torch.empty((B * N, C), dtype=torch.float32, device=dev)
+                u = torch.empty((B, N), dtype=torch.float32, device=dev)
+                for bi, gb in enumerate(generator):
+                    q[bi * N:(bi + 1) * N].exponential_(1, generator=gb)
+                    u[bi].uniform_(0, 1, generator=gb)
             else:
                 q = torch.empty((B * N, C), dtype=torch.float32, device=dev).exponential_(1, generator=generator)
                 u = None
@@ -106,9 +93,144 @@ class MMadaModelLM(LLaDAModelLM):
             if trace is not None:
                 trace.append(dict(step=step, cond=cond.view(B, N, C).clone(), uncond=None if unc is None else unc.view(B, N, C).clone(),
                                   sampled_ids=sampled, selected_probs=sel, masking=masking))
-        if caller_ids is not input_ids:
-            caller_ids.copy_(input_ids)                                          # keep the in-place contract
+            if caller_ids is not input_ids:
+                caller_ids.copy_(input_ids)                                      # keep the in-place contract
+            yield step, sampled
+
+    @torch.no_grad()
+    def t2i_generate(
+            self,
+            input_ids: torch.LongTensor = None,
+            uncond_input_ids: torch.LongTensor = None,
+            attention_mask=None,
+            uncond_attention_mask=None,
+            temperature=1.0,
+            timesteps=18,
+            guidance_scale=0,
+            noise_schedule=cosine_schedule,
+            generator: torch.Generator = None,
+            config=None,
+            seq_len=1024,
+            mask_token_id=126336,
+            resolution=512,
+            codebook_size=8192,
+            **kwargs,
+    ):
+        """MaskGIT-style parallel decoding with classifier-free guidance; returns (B, seq_len) int64
+        code ids and leaves ``input_ids`` mutated like the reference (:206).  Extra kwargs:
+        ``uni_prompting`` (only ``len(uni_prompting.text_tokenizer)`` is read, :149) and, for parity
+        tests, ``noise`` = per-step list of (q [B*N, C] ~ Exp(1), u [B, N] ~ U(0,1)).  The attention
+        masks are accepted and have no effect, as in the reference (Q1)."""
+        sampled = None
+        for _, sampled in self._t2i_steps(input_ids, uncond_input_ids, temperature, timesteps, guidance_scale,
+                                          noise_schedule, generator, seq_len, mask_token_id, resolution, codebook_size,
+                                          kwargs):
+            pass
         return sampled
+
+    def t2i_generate_decoding_stepwise(
+            self,
+            input_ids: torch.LongTensor = None,
+            uncond_input_ids: torch.LongTensor = None,
+            attention_mask=None,
+            uncond_attention_mask=None,
+            temperature=1.0,
+            timesteps=18,
+            guidance_scale=0,
+            noise_schedule=cosine_schedule,
+            generator: torch.Generator = None,
+            config=None,
+            seq_len=1024,
+            mask_token_id=126336,
+            resolution=512,
+            codebook_size=8192,
+            vq_model=None,
+            **kwargs,
+    ):
+        """Reference models/modeling_mmada.py:558-663: ``t2i_generate`` as a Python generator that also
+        decodes the current prediction of row 0 every step and yields ``(PIL.Image, "Step i/T")``.
+        (The reference decodes the whole batch and keeps image 0, :627-635; only row 0 is decoded here.)"""
+        from PIL import Image
+        with torch.no_grad():
+            for step, sampled in self._t2i_steps(input_ids, uncond_input_ids, temperature, timesteps, guidance_scale,
+                                                 noise_schedule, generator, seq_len, mask_token_id, resolution,
+                                                 codebook_size, kwargs):
+                codes = torch.clamp(sampled[:1], 0, 8192 - 1)
+                if hasattr(vq_model, "decode_code_uint8"):
+                    img = vq_model.decode_code_uint8(codes)[0].cpu().numpy()
+                else:                                    # any object with the reference's decode_code
+                    x = torch.clamp((vq_model.decode_code(codes) + 1.0) / 2.0, min=0.0, max=1.0) * 255.0
+                    img = x.permute(0, 2, 3, 1).cpu().numpy().astype("uint8")[0]
+                yield Image.fromarray(img), f"Step {step + 1}/{timesteps}"
+
+    @torch.no_grad()
+    def t2m_generate(
+            self,
+            input_ids: torch.LongTensor = None,
+            attention_mask=None,
+            temperature=1.0,
+            timesteps=18,
+            noise_schedule=cosine_schedule,
+            generator: torch.Generator = None,
+            config=None,
+            seq_len=256,
+            mask_token_id=126336,
+            motion_vocab_size=512,
+            num_new_special_tokens=0,
+            **kwargs,
+    ):
+        """Text-to-motion variant (reference models/modelling_ours.py:557-682): no CFG, motion vocabulary
+        slice [len(tokenizer)+image_codebook_size, +motion_vocab_size), non-compounding temperature, no
+        re-masking on the last step, returns the LAST step's raw samples (not merged with kept tokens,
+        Appendix A Q15).  ``input_ids`` is updated in place with offset token ids."""
+        uni_prompting = kwargs.get("uni_prompting", None)
+        noise = kwargs.get("noise", None)
+        dev = self.device
+        caller_ids = input_ids
+        input_ids = input_ids if input_ids.is_cuda else input_ids.to(dev)
+        B, L = input_ids.shape
+        start = end = None
+        spt = getattr(uni_prompting, "sptids_dict", None) if uni_prompting is not None else None
+        if spt is not None and "<|som|>" in spt and "<|eom|>" in spt:            # one host read, like the reference
+            som = (input_ids == int(spt["<|som|>"])).nonzero(as_tuple=True)[1]
+            eom = (input_ids == int(spt["<|eom|>"])).nonzero(as_tuple=True)[1]
+            if som.numel() > 0:
+                start = int(som[0]) + 1
+            if eom.numel() > 0:
+                end = int(eom[0])
+        if start is None or end is None:
+            start, end = L - seq_len, L
+        N = end - start
+        text_vocab = len(uni_prompting.text_tokenizer) if uni_prompting else 126000
+        offset = text_vocab + kwargs.get("image_codebook_size", 8192)
+        C = motion_vocab_size
+        local = input_ids[:, start:end]
+        known = torch.where(local == mask_token_id, mask_token_id, local - offset).contiguous()
+        rows = (torch.arange(B, device=dev, dtype=torch.int32)[:, None] * L + start
+                + torch.arange(N, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
+        tickets = torch.zeros(B, dtype=torch.int32, device=dev)
+        raw = None
+        for step in range(timesteps):
+            logits = self.logits_rows(input_ids, rows, offset, offset + C)                  # [B*N, C]
+            if noise is not None:
+                q, u = (t.to(dev) for t in noise[step])
+            else:
+                q = torch.empty((B * N, C), dtype=torch.float32, device=dev).exponential_(1, generator=generator)
+                u = None
+            last = step == timesteps - 1
+            ratio = 1.0 * (step + 1) / timesteps
+            mask_len_raw = float((seq_len * noise_schedule(torch.tensor(ratio))).floor())
+            if u is None:
+                u = torch.zeros((B, N), dtype=torch.float32, device=dev)
+                if not last:                                                               # the last step draws no u
+                    u.uniform_(0, 1, generator=generator)
+            _, _, _, raw = ops.t2i_sample_step(logits, None, q, u, known, input_ids, start, tickets, 0.0, mask_len_raw,
+                                               temperature * (1.0 - ratio), mask_token_id, offset, want_raw=True,
+                                               no_remask=last)
+            self.kernel_launches += 1
+        if caller_ids is not input_ids:
+            caller_ids.copy_(input_ids)
+        return raw
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

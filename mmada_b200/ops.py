@@ -110,10 +110,11 @@ def attention(qkv: torch.Tensor, batch: int, seq_len: int, n_heads: int, head_di
 def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch.Tensor, u: torch.Tensor,
                     known: torch.Tensor, input_ids: Optional[torch.Tensor], img_off: int, tickets: torch.Tensor,
                     guidance: float, mask_len_raw: float, temperature: float, mask_id: int, text_vocab: int,
-                    want_masking: bool = False):
+                    want_masking: bool = False, want_raw: bool = False, no_remask: bool = False):
     """One fused sampling step (see csrc/sampling.cu).  cond/uncond/q: fp32 [B*N, C]; u fp32 [B, N];
     known int64 [B, N] (updated in place); input_ids int64 [B, L] (image slice updated in place).
-    Returns (sampled_ids [B,N] int64, selected_probs [B,N] fp32, masking [B,N] bool or None)."""
+    Returns (sampled_ids [B,N] int64, selected_probs [B,N] fp32, masking [B,N] bool or None); with
+    ``want_raw`` a 4th element: the raw samples at every position (t2m_generate's return value)."""
     B, N = known.shape
     C = cond.shape[-1]
     for t, n in ((cond, "cond"), (q, "q"), (u, "u")):
@@ -132,11 +133,14 @@ def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch
     sampled = torch.empty((B, N), dtype=torch.int64, device=cond.device)
     sel = torch.empty((B, N), dtype=torch.float32, device=cond.device)
     masking = torch.empty((B, N), dtype=torch.uint8, device=cond.device) if want_masking else None
+    raw = torch.empty((B, N), dtype=torch.int64, device=cond.device) if want_raw else None
     # python scalars reach the tensor op as fp32 in the reference ((1 + g) * cond, g * uncond, T * gumbel)
     _lib.call("mmada_t2i_sample_step", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
-              _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking), tickets.data_ptr(),
-              B, N, C, float(1 + guidance), float(guidance), float(mask_len_raw), float(temperature), mask_id,
-              text_vocab, _stream())
+              _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking), _ptr(raw),
+              1 if no_remask else 0, tickets.data_ptr(), B, N, C, float(1 + guidance), float(guidance),
+              float(mask_len_raw), float(temperature), mask_id, text_vocab, _stream())
+    if want_raw:
+        return sampled, sel, (masking.bool() if want_masking else None), raw
     return sampled, sel, (masking.bool() if want_masking else None)
 
 

@@ -137,6 +137,61 @@ def t2i_generate(logits_fn: Callable[[torch.Tensor], torch.Tensor],
     return sampled
 
 
+# ---- MMadaModelLM.t2m_generate (models/modelling_ours.py:557-682) ---------------------------------
+
+def t2m_generate(logits_fn: Callable[[torch.Tensor], torch.Tensor], input_ids: torch.Tensor, *, temperature: float = 1.0,
+                 timesteps: int = 18, noise_schedule: Callable = cosine_schedule,
+                 generator: Optional[torch.Generator] = None, seq_len: int = 256, mask_token_id: int = 126336,
+                 motion_vocab_size: int = 512, text_vocab: int = 126349, image_codebook_size: int = 8192,
+                 som_token: Optional[int] = None, eom_token: Optional[int] = None,
+                 noise: Optional[Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]]] = None,
+                 trace: Optional[list] = None) -> torch.Tensor:
+    """No CFG, non-compounding temperature, no re-masking on the last step, returns the last step's raw
+    samples (Q15).  Mutates ``input_ids`` in place (offset token ids)."""
+    start = end = None
+    if som_token is not None:
+        pos = (input_ids == som_token).nonzero(as_tuple=True)
+        if len(pos[1]) > 0:
+            start = pos[1][0].item() + 1
+    if eom_token is not None:
+        pos = (input_ids == eom_token).nonzero(as_tuple=True)
+        if len(pos[1]) > 0:
+            end = pos[1][0].item()
+    if start is None or end is None:
+        start, end = input_ids.shape[1] - seq_len, input_ids.shape[1]
+    local = input_ids[:, start:end].clone()
+    off = text_vocab + image_codebook_size
+    sampled_ids = None
+    for step in range(timesteps):
+        logits = logits_fn(input_ids)
+        ml = logits[:, start:end, off:off + motion_vocab_size]
+        probs = ml.softmax(dim=-1)
+        flat = probs.reshape(-1, ml.size(-1))
+        if noise is not None:
+            q, u = noise[step]
+        else:
+            q, u = torch.empty_like(flat).exponential_(1, generator=generator), None
+        sampled_ids = torch.argmax(flat / q, dim=-1).view(*ml.shape[:-1])
+        merged = sampled_ids + off
+        unknown = local == mask_token_id
+        merged = torch.where(unknown, merged, local)
+        input_ids[:, start:end] = merged
+        masking = None
+        if step < timesteps - 1:
+            ratio = 1.0 * (step + 1) / timesteps
+            mask_ratio = noise_schedule(torch.tensor(ratio))
+            sel = torch.gather(probs, -1, sampled_ids.long()[..., None]).squeeze(-1)
+            sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
+            mask_len = (seq_len * mask_ratio).floor().unsqueeze(0).to(ml.device)
+            mask_len = torch.max(torch.tensor([1], device=ml.device), torch.min(unknown.sum(dim=-1, keepdim=True) - 1, mask_len))
+            masking = mask_by_random_topk(mask_len, sel, temperature * (1.0 - ratio), generator=generator, u=u)
+            local = torch.where(masking, mask_token_id, merged)
+            input_ids[:, start:end] = torch.where(masking, mask_token_id, merged)
+        if trace is not None:
+            trace.append(dict(step=step, logits=ml, q=q, u=u, sampled_ids=sampled_ids, merged=merged, masking=masking))
+    return sampled_ids
+
+
 # ---- generate.py / mmu_generate -------------------------------------------------------------
 
 def add_gumbel_noise(logits: torch.Tensor, temperature: float, u: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -118,6 +118,42 @@ def text_case(name, cfg, B, Lp, gen, block, steps, temperature, cfg_scale, wseed
           temperature=np.array(temperature), cfg_scale=np.array(cfg_scale), **extra)
 
 
+def t2m_case(name, cfg, B, Lt, N, steps, wseed, seed, gseed):
+    """t2m_generate of the reference's fork models/modelling_ours.py (BASELINE configs[4])."""
+    import importlib
+    print(f"[t2m] {name}")
+    rb.modules()
+    mo = importlib.import_module("models.modelling_ours")
+    sd = W.make_llada_weights(cfg, wseed)
+    base = rb.build_model(cfg, sd)
+    # the fork's class has the same constructor; reuse the loaded reference model's weights
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = mo.MMadaModelLM(base.config, init_params=False).eval()
+    model.load_state_dict(base.state_dict())
+    g = torch.Generator().manual_seed(seed)
+    som, eom = 126096, 126097
+    text = torch.randint(0, 126000, (B, Lt), generator=g)
+    ids = torch.cat([text, torch.full((B, 1), som), torch.full((B, N), 126336), torch.full((B, 1), eom)], 1)
+
+    class UP(rb.UniPromptingStub):
+        sptids_dict = {"<|som|>": torch.tensor([som]), "<|eom|>": torch.tensor([eom])}
+
+    ids_ref = ids.clone()
+    out_ref = model.t2m_generate(input_ids=ids_ref, timesteps=steps, seq_len=N, generator=torch.Generator().manual_seed(gseed),
+                                 uni_prompting=UP(W.TEXT_VOCAB))
+    ids_or = ids.clone()
+    trace = []
+    out_or = denoise.t2m_generate(lambda x: llada.forward_logits(x, sd, cfg), ids_or, timesteps=steps, seq_len=N,
+                                  generator=torch.Generator().manual_seed(gseed), som_token=som, eom_token=eom, trace=trace)
+    assert torch.equal(out_ref, out_or), "restatement != reference (t2m sampled_ids)"
+    assert torch.equal(ids_ref, ids_or), "restatement != reference (t2m input_ids)"
+    _save(name, ids=ids, sampled_ids=out_ref, final_input_ids=ids_ref,
+          step_merged=torch.stack([t["merged"] for t in trace]),
+          step_masking=torch.stack([t["masking"] for t in trace[:-1]]),
+          meta=np.array([B, Lt, N, steps, wseed, seed, gseed]))
+
+
 def sampling_case():
     print("[sampling]")
     _, _, sp, _ = rb.modules()
@@ -211,6 +247,7 @@ def main():
               wseed=0, seed=22, fast_eot="miss")
     text_case("text_cfg", W.TINY, B=2, Lp=10, gen=32, block=16, steps=8, temperature=0.7, cfg_scale=1.5,
               wseed=0, seed=23)
+    t2m_case("t2m_tiny", W.TINY, B=2, Lt=20, N=64, steps=6, wseed=0, seed=31, gseed=77)
     if "--skip-c1" not in sys.argv:
         t2i_case("t2i_c1", W.C1, B=1, P=129, N=256, steps=15, guidance=3.5, wseed=0, pseed=0, gseed=1234)
 

@@ -88,3 +88,61 @@ def test_t2i_generate_decisions_match_oracle(golden, name, cfgname):
     print(f"{name}: first-step logits err {err:.3e}; sampled-id agreement with the fp32 reference run: "
           f"step0 {agree0:.3f}, final {agree:.3f}")
     assert err < TOL
+
+
+def test_t2m_generate_decisions_match_oracle(golden):
+    """t2m_generate (reference fork models/modelling_ours.py:557-682): raw last-step samples returned,
+    no re-masking on the last step, non-compounding temperature — replayed on the oracle with the CUDA
+    path's logits and the same noise."""
+    from oracle import denoise, weights as W
+    gd = golden("t2m_tiny")
+    B, Lt, N, steps, wseed, seed, gseed = (int(v) for v in gd["meta"])
+    m = _model(W.TINY, wseed)
+    ids0 = torch.from_numpy(gd["ids"])
+    g = torch.Generator().manual_seed(gseed)
+    noise = []
+    for s in range(steps):
+        q = torch.empty(B * N, 512).exponential_(1, generator=g)
+        u = torch.zeros(B, N).uniform_(0, 1, generator=g) if s < steps - 1 else torch.zeros(B, N)
+        noise.append((q, u))
+
+    class UP(_UP):
+        sptids_dict = {"<|som|>": torch.tensor([126096]), "<|eom|>": torch.tensor([126097])}
+
+    ids = ids0.clone().cuda()
+    out = m.t2m_generate(input_ids=ids, timesteps=steps, seq_len=N, uni_prompting=UP(), noise=noise)
+    # oracle replay: logits from the CUDA model itself (full forward, sliced), same noise
+    off = W.TEXT_VOCAB + 8192
+    ido = ids0.clone()
+    outo = denoise.t2m_generate(lambda x: m(x.cuda()).logits.float().cpu(), ido, timesteps=steps, seq_len=N,
+                                som_token=126096, eom_token=126097, noise=noise)
+    assert torch.equal(out.cpu(), outo)
+    assert torch.equal(ids.cpu(), ido)
+    assert int((ids == 126336).sum()) == 0
+    assert out.min() >= 0 and out.max() < 512
+    agree = float((out.cpu() == torch.from_numpy(gd["sampled_ids"])).float().mean())
+    print(f"t2m_tiny: agreement with the fp32 reference run {agree:.3f}")
+
+
+def test_t2i_stepwise_yields_images():
+    from mmada_b200.modeling_magvitv2 import MAGVITv2
+    from oracle import weights as W
+    m = _model(W.TINY, 0)
+    vq = MAGVITv2().load_state_dict(W.make_vq_decoder_weights(0))
+    B, P, N, steps = 1, 17, 256, 3
+    cond, unc, _, _ = W.make_t2i_prompts(B, P, N, 3)
+    g1 = torch.Generator(device="cuda").manual_seed(5)
+    ids1 = cond.clone().cuda()
+    frames = list(m.t2i_generate_decoding_stepwise(input_ids=ids1, uncond_input_ids=unc.cuda(), guidance_scale=2.0,
+                                                   timesteps=steps, seq_len=N, resolution=P - 1, generator=g1,
+                                                   uni_prompting=_UP(), vq_model=vq))
+    assert [t for _, t in frames] == [f"Step {i + 1}/{steps}" for i in range(steps)]
+    assert frames[0][0].size == (256, 256) and frames[0][0].mode == "RGB"
+    # same generator seed through t2i_generate: identical final state
+    ids2 = cond.clone().cuda()
+    out = m.t2i_generate(input_ids=ids2, uncond_input_ids=unc.cuda(), guidance_scale=2.0, timesteps=steps, seq_len=N,
+                         resolution=P - 1, generator=torch.Generator(device="cuda").manual_seed(5), uni_prompting=_UP())
+    assert torch.equal(ids1, ids2)
+    import numpy as np
+    last = np.asarray(frames[-1][0])
+    assert np.array_equal(last, vq.decode_code_uint8(out[:1].clamp(0, 8191))[0].cpu().numpy())

@@ -93,3 +93,15 @@ def test_magvit(golden):
     pix = magvit.decode_code(torch.from_numpy(gd["idx_8x8"]), sd, taps)
     assert np.array_equal(pix.numpy(), gd["pix_8x8"])
     assert list(taps.keys()) == list(gd["tap_names_8x8"])
+
+
+def test_t2m_tiny(golden):
+    gd = golden("t2m_tiny")
+    B, Lt, N, steps, wseed, seed, gseed = (int(v) for v in gd["meta"])
+    sd = W.make_llada_weights(W.TINY, wseed)
+    ids = torch.from_numpy(gd["ids"]).clone()
+    out = denoise.t2m_generate(lambda x: llada.forward_logits(x, sd, W.TINY), ids, timesteps=steps, seq_len=N,
+                               generator=torch.Generator().manual_seed(gseed), som_token=126096, eom_token=126097)
+    assert np.array_equal(out.numpy(), gd["sampled_ids"])
+    assert np.array_equal(ids.numpy(), gd["final_input_ids"])
+    assert int((ids == 126336).sum()) == 0            # Q15: no re-masking on the last step
