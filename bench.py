@@ -244,7 +244,7 @@ def run_own(args):
 
     # ---- end to end through the public API, host buffers in, host results out
     G = max(1, K // STEPS_PER_IMAGE)
-    out_h = torch.empty((B, 3, 512, 512) if vq is not None else (B, N_IMG),
+    out_h = torch.empty((B, 512, 512, 3) if vq is not None else (B, N_IMG),
                         dtype=torch.uint8 if vq is not None else torch.int64).pin_memory()
     barrier()
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from . import generate as _generate
+from .generate import generate as _generate_fn
 from .modeling_llada import CausalLMOutput, LLaDAConfig, LLaDAModelLM
 from .sampling import cosine_schedule
 
@@ -239,7 +239,7 @@ class MMadaModelLM(LLaDAModelLM):
                      mask_id=126336, attention_mask=None, **kwargs):
         """Reference models/modeling_mmada.py:388-481: the same algorithm as ``generate()``.  ``top_k``,
         ``input_embeddings`` and ``eot_token`` are accepted and ignored like the reference (Q14)."""
-        return _generate.generate(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
+        return _generate_fn(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
                                   temperature=temperature, cfg_scale=cfg_scale, remasking=remasking, mask_id=mask_id,
                                   attention_mask=attention_mask, **kwargs)
 
@@ -249,6 +249,6 @@ class MMadaModelLM(LLaDAModelLM):
                           mask_id=126336, attention_mask=None, **kwargs):
         """Reference :483-556: ``mmu_generate`` plus an early exit once every row's block-final token is
         ``eot_token`` (one device->host read per block, as in the reference)."""
-        return _generate.generate(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
+        return _generate_fn(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
                                   temperature=temperature, cfg_scale=cfg_scale, remasking=remasking, mask_id=mask_id,
                                   attention_mask=attention_mask, eot_token=eot_token, **kwargs)

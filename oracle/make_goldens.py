@@ -247,7 +247,7 @@ def main():
               wseed=0, seed=22, fast_eot="miss")
     text_case("text_cfg", W.TINY, B=2, Lp=10, gen=32, block=16, steps=8, temperature=0.7, cfg_scale=1.5,
               wseed=0, seed=23)
-    t2m_case("t2m_tiny", W.TINY, B=2, Lt=20, N=64, steps=6, wseed=0, seed=31, gseed=77)
+    t2m_case("t2m_tiny", W.TINY_T2M, B=2, Lt=20, N=64, steps=6, wseed=0, seed=31, gseed=77)
     if "--skip-c1" not in sys.argv:
         t2i_case("t2i_c1", W.C1, B=1, P=129, N=256, steps=15, guidance=3.5, wseed=0, pseed=0, gseed=1234)
 

@@ -35,6 +35,8 @@ C2 = dict(d_model=4096, n_heads=32, n_layers=32, mlp_hidden_size=12288, vocab_si
 TINY = dict(d_model=256, n_heads=4, n_layers=2, mlp_hidden_size=512, vocab_size=134656,
             rope_theta=500000.0, rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
 TINY128 = dict(TINY, d_model=512, n_heads=4, mlp_hidden_size=1024)
+#: text-to-motion: the vocabulary must hold text + 8192 image codes + 512 motion codes
+TINY_T2M = dict(TINY, vocab_size=135168)
 
 #: `len(uni_prompting.text_tokenizer)` stand-in (reference app.py:396); image code c has id c + this.
 TEXT_VOCAB = 126349

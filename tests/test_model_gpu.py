@@ -97,7 +97,7 @@ def test_t2m_generate_decisions_match_oracle(golden):
     from oracle import denoise, weights as W
     gd = golden("t2m_tiny")
     B, Lt, N, steps, wseed, seed, gseed = (int(v) for v in gd["meta"])
-    m = _model(W.TINY, wseed)
+    m = _model(W.TINY_T2M, wseed)
     ids0 = torch.from_numpy(gd["ids"])
     g = torch.Generator().manual_seed(gseed)
     noise = []

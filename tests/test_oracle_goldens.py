@@ -98,9 +98,9 @@ def test_magvit(golden):
 def test_t2m_tiny(golden):
     gd = golden("t2m_tiny")
     B, Lt, N, steps, wseed, seed, gseed = (int(v) for v in gd["meta"])
-    sd = W.make_llada_weights(W.TINY, wseed)
+    sd = W.make_llada_weights(W.TINY_T2M, wseed)
     ids = torch.from_numpy(gd["ids"]).clone()
-    out = denoise.t2m_generate(lambda x: llada.forward_logits(x, sd, W.TINY), ids, timesteps=steps, seq_len=N,
+    out = denoise.t2m_generate(lambda x: llada.forward_logits(x, sd, W.TINY_T2M), ids, timesteps=steps, seq_len=N,
                                generator=torch.Generator().manual_seed(gseed), som_token=126096, eom_token=126097)
     assert np.array_equal(out.numpy(), gd["sampled_ids"])
     assert np.array_equal(ids.numpy(), gd["final_input_ids"])
