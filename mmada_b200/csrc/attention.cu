@@ -36,6 +36,25 @@ struct AttnParams {
     float scale_log2;      // softmax scale * log2(e)
 };
 
+// 2^x on the MUFU pipe (one instruction; flush-to-zero, -inf -> 0)
+__device__ __forceinline__ float ex2_mufu(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 2^x on the FMA pipe: floor via the 1.5*2^23 magic add (round-down), degree-3 minimax polynomial of 2^f on
+// [0,1), exponent patched in with an integer add.  Relative error ~1e-4 — P is rounded to bf16 (2^-9) anyway.
+// Part of every row goes through here so that the MUFU pipe (16 ex2/clk/SM) is not the softmax bottleneck.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float r = __fadd_rd(x, 12582912.0f);
+    const float f = x - (r - 12582912.0f);
+    float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+    p = fmaf(p, f, 0.695146143436431885f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 template <int HD>
 struct AttnCfg {
     static constexpr int TILE_BYTES = QT * HD * 2;          // one Q / K / V tile
@@ -231,7 +250,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 if (j == 0) {
                     m_used = m_new;
                 } else if (__any_sync(0xffffffffu, grow)) {
-                    const float alpha = grow ? exp2f((m_used - m_new) * p.scale_log2) : 1.0f;
+                    const float alpha = grow ? ex2_mufu((m_used - m_new) * p.scale_log2) : 1.0f;
                     if (grow) m_used = m_new;
                     l_sum *= alpha;
 #pragma unroll 1
@@ -254,8 +273,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         uint32_t pw[16];
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
-                            const float e0 = exp2f(fmaf(__uint_as_float(sv[c * 32 + 2 * t]), p.scale_log2, -mb));
-                            const float e1 = exp2f(fmaf(__uint_as_float(sv[c * 32 + 2 * t + 1]), p.scale_log2, -mb));
+                            const float x0 = fmaf(__uint_as_float(sv[c * 32 + 2 * t]), p.scale_log2, -mb);
+                            const float x1 = fmaf(__uint_as_float(sv[c * 32 + 2 * t + 1]), p.scale_log2, -mb);
+                            const float e0 = ex2_mufu(x0);
+                            const float e1 = (t & 1) ? ex2_poly(x1) : ex2_mufu(x1);     // every 4th element on the FMA pipe
                             rs += e0 + e1;
                             pw[t] = pack_bf16(e0, e1);
                         }

@@ -51,7 +51,9 @@ struct GemmCfg {
     static constexpr int B_BYTES = LOAD_N * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 8 ? 8 : (196 * 1024 / STAGE_BYTES);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES + 256;       // after the barriers
+    static constexpr int STAGING_BYTES = 4 * 32 * 144;                   // 4 epilogue warps x 32 rows x (128 + 16) B
+    static constexpr int SMEM_BYTES = STAGING_OFF + STAGING_BYTES + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int& mt, int& nt) {
@@ -118,6 +120,38 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int co
                 }
         }
     }
+}
+
+// Transposes a 32-row x ROW_BYTES block (one row per lane, `w` = the lane's row as 32-bit words) through
+// the warp's private staging buffer and writes it with coalesced 16-byte stores: one warp instruction
+// covers 32/PIECES whole rows instead of 16 bytes of 32 different rows.  RESID adds an fp32 residual.
+template <int ROW_BYTES, bool RESID>
+__device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, uint8_t* gptr, const uint8_t* rptr,
+                                             int64_t pitch_bytes, int rows_valid, int lane) {
+    constexpr int PITCH = ROW_BYTES + 16;        // +16: conflict-free 128-bit accesses in both directions
+    constexpr int PIECES = ROW_BYTES / 16;
+    constexpr int RPI = 32 / PIECES;
+#pragma unroll
+    for (int j = 0; j < PIECES; ++j)
+        *reinterpret_cast<uint4*>(stage + lane * PITCH + j * 16) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    __syncwarp();
+    const int piece = lane % PIECES, rsub = lane / PIECES;
+#pragma unroll
+    for (int i = 0; i < 32 / RPI; ++i) {
+        const int r = i * RPI + rsub;
+        uint4 v = *reinterpret_cast<const uint4*>(stage + r * PITCH + piece * 16);
+        if (r < rows_valid) {
+            if constexpr (RESID) {
+                const float4 b = *reinterpret_cast<const float4*>(rptr + (int64_t)r * pitch_bytes + piece * 16);
+                v.x = __float_as_uint(__uint_as_float(v.x) + b.x);
+                v.y = __float_as_uint(__uint_as_float(v.y) + b.y);
+                v.z = __float_as_uint(__uint_as_float(v.z) + b.z);
+                v.w = __float_as_uint(__uint_as_float(v.w) + b.w);
+            }
+            *reinterpret_cast<uint4*>(gptr + (int64_t)r * pitch_bytes + piece * 16) = v;
+        }
+    }
+    __syncwarp();
 }
 
 template <int CG, int EPI, int BN, bool CONV>
@@ -264,34 +298,78 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            uint8_t* stage = smem + Cfg::STAGING_OFF + (warp - 2) * (32 * 144);
+            const int row0 = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32;       // first row of this warp
+            const int rows_valid = min(32, p.M - row0);
+            constexpr int OUT_ES = epi_out_bf16(EPI) ? 2 : 4;
+            const int64_t pitch = p.ldo * OUT_ES;
+            const bool vec_ok = (pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                                (!epi_has_resid(EPI) || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
             if constexpr (EPI == MMADA_EPI_SWIGLU_BF16) {
                 // columns [0,BN/2) = gate, [BN/2,BN) = up for output columns nt*BN/2 + [0,BN/2)
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)row * p.ldo + nt * (BN / 2);
+                uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)nt * (BN / 2) * 2;
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(t_addr + c * 32, g);
                     tmem_ld_32x32b_x32(t_addr + BN / 2 + c * 32, u);
                     tmem_ld_wait();
-                    if (row < p.M) {
+                    uint32_t w[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float f[8];
+                    for (int j = 0; j < 16; ++j)
+                        w[j] = pack_bf16(silu_f(__uint_as_float(g[2 * j])) * __uint_as_float(u[2 * j]),
+                                         silu_f(__uint_as_float(g[2 * j + 1])) * __uint_as_float(u[2 * j + 1]));
+                    if (rows_valid > 0) staged_store<64, false>(stage, w, obase + c * 64, nullptr, pitch, rows_valid, lane);
+                }
+            } else if constexpr (epi_out_bf16(EPI)) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 64; ++c) {
+                    const int col0 = nt * BN + c * 64;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 64, v0);
+                    tmem_ld_32x32b_x32(t_addr + c * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (vec_ok && col0 + 64 <= p.N) {
+                        uint32_t w[32];
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                f[q] = silu_f(__uint_as_float(g[8 * j + q])) * __uint_as_float(u[8 * j + q]);
-                            *reinterpret_cast<uint4*>(o + c * 32 + 8 * j) = make_uint4(
-                                pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        for (int j = 0; j < 16; ++j) {
+                            float a0 = __uint_as_float(v0[2 * j]), a1 = __uint_as_float(v0[2 * j + 1]);
+                            float b0 = __uint_as_float(v1[2 * j]), b1 = __uint_as_float(v1[2 * j + 1]);
+                            if constexpr (epi_has_bias(EPI)) {
+                                a0 += __ldg(p.bias + col0 + 2 * j); a1 += __ldg(p.bias + col0 + 2 * j + 1);
+                                b0 += __ldg(p.bias + col0 + 32 + 2 * j); b1 += __ldg(p.bias + col0 + 33 + 2 * j);
+                            }
+                            w[j] = pack_bf16(a0, a1);
+                            w[16 + j] = pack_bf16(b0, b1);
                         }
+                        if (rows_valid > 0)
+                            staged_store<128, false>(stage, w, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 2,
+                                                     nullptr, pitch, rows_valid, lane);
+                    } else {
+                        store_chunk<EPI>(p, row, col0, v0);
+                        store_chunk<EPI>(p, row, col0 + 32, v1);
                     }
                 }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = nt * BN + c * 32;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_addr + c * 32, v);
                     tmem_ld_wait();
-                    store_chunk<EPI>(p, row, nt * BN + c * 32, v);
+                    if (vec_ok && col0 + 32 <= p.N) {
+                        if constexpr (epi_has_bias(EPI)) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + col0 + j));
+                        }
+                        if (rows_valid > 0)
+                            staged_store<128, epi_has_resid(EPI)>(
+                                stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4,
+                                reinterpret_cast<const uint8_t*>(p.aux) + (int64_t)row0 * pitch + (int64_t)col0 * 4, pitch,
+                                rows_valid, lane);
+                    } else {
+                        store_chunk<EPI>(p, row, col0, v);
+                    }
                 }
             }
             tc_fence_before();
