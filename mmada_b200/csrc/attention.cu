@@ -55,6 +55,27 @@ __device__ __forceinline__ float ex2_poly(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 
+// packed fp32x2 arithmetic (sm_100): two lanes per instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
 template <int HD>
 struct AttnCfg {
     static constexpr int TILE_BYTES = QT * HD * 2;          // one Q / K / V tile
@@ -241,9 +262,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     for (int c = 0; c < 128; ++c)
                         if (c >= keys) sv[c] = 0xff800000u;   // -inf: masked (or never written) key
                 }
-                float mx = -INFINITY;
+                float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // 4 independent chains
 #pragma unroll
-                for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+                for (int c = 0; c < 128; c += 8) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        mxa[t] = fmaxf(mxa[t], fmaxf(__uint_as_float(sv[c + 2 * t]), __uint_as_float(sv[c + 2 * t + 1])));
+                }
+                const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
                 // lazy rescale: keep the stale reference max unless it grows by more than 2^8
                 const float m_new = fmaxf(m_used, mx);
                 const bool grow = (m_new - m_used) * p.scale_log2 > 8.0f;
@@ -265,7 +291,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     tmem_st_wait();
                 }
                 const float mb = m_used * p.scale_log2;
-                float rs = 0.f;
+                const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nmb2 = make_float2(-mb, -mb);
+                float2 rs2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
                 // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -273,17 +300,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         uint32_t pw[16];
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
-                            const float x0 = fmaf(__uint_as_float(sv[c * 32 + 2 * t]), p.scale_log2, -mb);
-                            const float x1 = fmaf(__uint_as_float(sv[c * 32 + 2 * t + 1]), p.scale_log2, -mb);
-                            const float e0 = ex2_mufu(x0);
-                            const float e1 = (t & 1) ? ex2_poly(x1) : ex2_mufu(x1);     // every 4th element on the FMA pipe
-                            rs += e0 + e1;
-                            pw[t] = pack_bf16(e0, e1);
+                            // packed fp32x2: one FFMA2 scales-and-shifts two scores, one FADD2 adds two exponentials
+                            const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 32 + 2 * t]), __uint_as_float(sv[c * 32 + 2 * t + 1])),
+                                                   sc2, nmb2);
+                            const float2 e = make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
+                            rs2[t & 3] = fadd2(rs2[t & 3], e);
+                            pw[t] = pack_bf16(e.x, e.y);
                         }
                         tmem_st_32x32b_x16(t_s + c * 16, pw);
                     }
                 }
-                l_sum += rs;
+                l_sum += (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y) + (rs2[2].x + rs2[2].y) + (rs2[3].x + rs2[3].y);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(p_full(i));

@@ -295,6 +295,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             int mt, nt;
             tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
             const int row = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32 + lane;
+            if constexpr (epi_has_resid(EPI)) {
+                // the residual tile is read after the accumulator arrives: pull this thread's row segment into L2
+                // now (the warp is idle until then) so the epilogue's loads are L2 hits, not DRAM round trips
+                if (row < p.M && nt * BN + BN <= p.N)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const float*>(p.aux) +
+                                                                                      (int64_t)row * p.ldo + nt * BN),
+                                 "r"(BN * 4)
+                                 : "memory");
+            }
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
