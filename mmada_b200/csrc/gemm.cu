@@ -126,7 +126,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int co
 // the warp's private staging buffer and writes it with coalesced 16-byte stores: one warp instruction
 // covers 32/PIECES whole rows instead of 16 bytes of 32 different rows.  RESID adds an fp32 residual.
 template <int ROW_BYTES, bool RESID>
-__device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, uint8_t* gptr, const uint8_t* rptr,
+__device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, uint8_t* gptr, const float4* resid,
                                              int64_t pitch_bytes, int rows_valid, int lane) {
     constexpr int PITCH = ROW_BYTES + 16;        // +16: conflict-free 128-bit accesses in both directions
     constexpr int PIECES = ROW_BYTES / 16;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, 
         uint4 v = *reinterpret_cast<const uint4*>(stage + r * PITCH + piece * 16);
         if (r < rows_valid) {
             if constexpr (RESID) {
-                const float4 b = *reinterpret_cast<const float4*>(rptr + (int64_t)r * pitch_bytes + piece * 16);
+                const float4 b = resid[i];          // loaded one chunk ahead by the caller (same lane -> (row, piece) map)
                 v.x = __float_as_uint(__uint_as_float(v.x) + b.x);
                 v.y = __float_as_uint(__uint_as_float(v.y) + b.y);
                 v.z = __float_as_uint(__uint_as_float(v.z) + b.z);
@@ -295,18 +295,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             int mt, nt;
             tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
             const int row = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32 + lane;
-            if constexpr (epi_has_resid(EPI)) {
-                // the residual tile is read after the accumulator arrives: pull this thread's row segment into L2
-                // now (the warp is idle until then) so the epilogue's loads are L2 hits, not DRAM round trips
-                if (row < p.M && nt * BN + BN <= p.N)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const float*>(p.aux) +
-                                                                                      (int64_t)row * p.ldo + nt * BN),
-                                 "r"(BN * 4)
-                                 : "memory");
-            }
-            mbar_wait(tfull_bar(acc), acc_phase, 4);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
             uint8_t* stage = smem + Cfg::STAGING_OFF + (warp - 2) * (32 * 144);
             const int row0 = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32;       // first row of this warp
             const int rows_valid = min(32, p.M - row0);
@@ -314,6 +302,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int64_t pitch = p.ldo * OUT_ES;
             const bool vec_ok = (pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                                 (!epi_has_resid(EPI) || (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+            // residual: each lane reads the (row, 16-byte piece) it will write after the smem transpose, one
+            // 32-column chunk ahead of the accumulator — chunk 0 before the accumulator even exists, so the
+            // DRAM/L2 latency of the read-modify-write never sits on the epilogue's critical path
+            float4 rcur[8], rnext[8];
+            const uint8_t* rbase = reinterpret_cast<const uint8_t*>(p.aux) + (int64_t)row0 * pitch + (int64_t)nt * BN * 4;
+            auto load_resid = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3);
+                    dst[i] = (r < rows_valid) ? *reinterpret_cast<const float4*>(rbase + (int64_t)r * pitch + c * 128 + (lane & 7) * 16)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            const bool resid_vec = epi_has_resid(EPI) && vec_ok && nt * BN + BN <= p.N;
+            if constexpr (epi_has_resid(EPI)) {
+                if (resid_vec) load_resid(0, rcur);
+            }
+            mbar_wait(tfull_bar(acc), acc_phase, 4);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
             if constexpr (EPI == MMADA_EPI_SWIGLU_BF16) {
                 // columns [0,BN/2) = gate, [BN/2,BN) = up for output columns nt*BN/2 + [0,BN/2)
                 uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)nt * (BN / 2) * 2;
@@ -365,19 +373,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     const int col0 = nt * BN + c * 32;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_addr + c * 32, v);
+                    if constexpr (epi_has_resid(EPI)) {
+                        if (resid_vec && c + 1 < BN / 32) load_resid(c + 1, rnext);
+                    }
                     tmem_ld_wait();
-                    if (vec_ok && col0 + 32 <= p.N) {
+                    if (vec_ok && col0 + 32 <= p.N && (!epi_has_resid(EPI) || resid_vec)) {
                         if constexpr (epi_has_bias(EPI)) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + col0 + j));
                         }
                         if (rows_valid > 0)
                             staged_store<128, epi_has_resid(EPI)>(
-                                stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4,
-                                reinterpret_cast<const uint8_t*>(p.aux) + (int64_t)row0 * pitch + (int64_t)col0 * 4, pitch,
+                                stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4, rcur, pitch,
                                 rows_valid, lane);
                     } else {
                         store_chunk<EPI>(p, row, col0, v);
+                    }
+                    if constexpr (epi_has_resid(EPI)) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
                     }
                 }
             }
