@@ -25,9 +25,10 @@
 
 namespace mmada {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;   // 16 softmax warps + TMA warp + MMA warp; 576 x 112 registers fit the SM
 constexpr int QT = 128;    // query rows per tile
 constexpr int KT = 128;    // keys per tile
+constexpr int TMA_WARP = 16, MMA_WARP = 17;
 
 struct AttnParams {
     __nv_bfloat16* out;
@@ -85,13 +86,14 @@ struct AttnCfg {
     static constexpr int K_OFF = 2 * TILE_BYTES;            // 2 stages
     static constexpr int V_OFF = 4 * TILE_BYTES;            // 2 stages
     static constexpr int BAR_OFF = 6 * TILE_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int XCHG_OFF = BAR_OFF + 256;          // float [2 parity][2 tiles][2 halves][128 rows]
+    static constexpr int SMEM_BYTES = XCHG_OFF + 2 * 2 * 2 * 128 * 4 + 1024;
     static constexpr int TM_S = 0;                          // S_i at TM_S + 128 i
     static constexpr int TM_O = 256;                        // O_i at TM_O + HD i
 };
 
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __maxnreg__(112)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
     using Cfg = AttnCfg<HD>;
@@ -122,7 +124,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int tail = p.L - (n_kv - 1) * KT;                 // valid keys in the last tile (1..128)
     const int tail16 = (tail + 15) & ~15;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == TMA_WARP && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_k);
         tma_prefetch_desc(&map_v);
@@ -133,12 +135,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_init(v_full(s), 1);
             mbar_init(v_empty(s), 1);
             mbar_init(s_full(s), 1);
-            mbar_init(p_full(s), 128);
+            mbar_init(p_full(s), 256);
             mbar_init(o_full(s), 1);
         }
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == MMA_WARP) {
         tmem_alloc<1>(tmem_ptr_addr, 512);
         tmem_relinquish<1>();
     }
@@ -147,7 +149,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
 
-    if (warp == 8) {
+    // register re-balancing (setmaxnreg works per warpgroup): the 4 softmax warpgroups take what the
+    // TMA / MMA warpgroup does not need
+    if (warp == TMA_WARP) {
         // ======================================= TMA producer =======================================
         // the whole warp walks the loop (uniform addresses), one elected lane issues
         if (elect_one()) {
@@ -178,7 +182,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             __syncwarp();
         }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
         // ======================================= MMA issuer =======================================
         // the whole warp walks the schedule and waits; one elected lane issues MMAs and commits
         const uint64_t kdesc_hi = umma_desc_kmajor_sw128(0);
@@ -239,37 +243,51 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
     } else {
         // ======================================= softmax =======================================
-        const int i = warp >> 2;                        // query tile of this warpgroup
+        // 256 threads per query tile: the row's 128 scores are split between two threads (two warps on the
+        // same TMEM lane quarter), each owning 64 key columns and half of the output columns.  The halves
+        // exchange their row maxima through shared memory once per tile (one 256-thread named barrier) and
+        // their row sums once at the end.  A single thread per row was measured latency-bound (~3000 cycles
+        // of dependent instructions per tile against 1024 cycles of MMA).
+        const int i = warp >> 3;                        // query tile
+        const int half = (warp >> 2) & 1;               // which 64 keys / which half of the head dim
         const int quarter = warp & 3;
         if (i < n_qt) {
             const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
             const uint32_t t_s = tmem + Cfg::TM_S + 128 * i + lane_off;
-            const uint32_t t_o = tmem + Cfg::TM_O + HD * i + lane_off;
-            const int qrow = q0 + i * QT + quarter * 32 + lane;
+            const uint32_t t_o = tmem + Cfg::TM_O + HD * i + half * (HD / 2) + lane_off;
+            const int rloc = quarter * 32 + lane;
+            const int qrow = q0 + i * QT + rloc;
+            float* xchg = reinterpret_cast<float*>(smem + Cfg::XCHG_OFF);
+            auto xslot = [&](int par, int hf) { return xchg + ((par * 2 + i) * 2 + hf) * 128 + rloc; };
             float m_used = -INFINITY, l_sum = 0.f;
             for (int j = 0; j < n_kv; ++j) {
                 const int keys = (j == n_kv - 1) ? tail : KT;          // valid keys
                 const int keys16 = (keys + 15) & ~15;
+                const int kbase = 64 * half;                            // first key of this thread's half
                 mbar_wait(s_full(i), j & 1, 30);
                 tc_fence_after();
-                uint32_t sv[128];
+                uint32_t sv[64];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c * 32 < keys16) tmem_ld_32x32b_x32(t_s + c * 32, &sv[c * 32]);
+                for (int c = 0; c < 2; ++c) {
+                    if (kbase + c * 32 < keys16) tmem_ld_32x32b_x32(t_s + kbase + c * 32, &sv[c * 32]);
+                }
                 tmem_ld_wait();
                 if (keys < KT) {
 #pragma unroll
-                    for (int c = 0; c < 128; ++c)
-                        if (c >= keys) sv[c] = 0xff800000u;   // -inf: masked (or never written) key
+                    for (int c = 0; c < 64; ++c)
+                        if (kbase + c >= keys) sv[c] = 0xff800000u;   // -inf: masked (or never written) key
                 }
                 float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // 4 independent chains
 #pragma unroll
-                for (int c = 0; c < 128; c += 8) {
+                for (int c = 0; c < 64; c += 8) {
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
                         mxa[t] = fmaxf(mxa[t], fmaxf(__uint_as_float(sv[c + 2 * t]), __uint_as_float(sv[c + 2 * t + 1])));
                 }
-                const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+                float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+                *xslot(j & 1, half) = mx;
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
+                mx = fmaxf(mx, *xslot(j & 1, half ^ 1));
                 // lazy rescale: keep the stale reference max unless it grows by more than 2^8
                 const float m_new = fmaxf(m_used, mx);
                 const bool grow = (m_new - m_used) * p.scale_log2 > 8.0f;
@@ -280,7 +298,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     if (grow) m_used = m_new;
                     l_sum *= alpha;
 #pragma unroll 1
-                    for (int c = 0; c < HD / 16; ++c) {
+                    for (int c = 0; c < HD / 32; ++c) {                 // this thread's half of the output columns
                         uint32_t ov[16];
                         tmem_ld_32x32b_x16(t_o + c * 16, ov);
                         tmem_ld_wait();
@@ -295,8 +313,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 float2 rs2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
                 // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c * 32 < keys16) {
+                for (int c = 0; c < 2; ++c) {
+                    if (kbase + c * 32 < keys16) {
                         uint32_t pw[16];
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
@@ -307,7 +325,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             rs2[t & 3] = fadd2(rs2[t & 3], e);
                             pw[t] = pack_bf16(e.x, e.y);
                         }
-                        tmem_st_32x32b_x16(t_s + c * 16, pw);
+                        tmem_st_32x32b_x16(t_s + (kbase >> 1) + c * 16, pw);
                     }
                 }
                 l_sum += (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y) + (rs2[2].x + rs2[2].y) + (rs2[3].x + rs2[3].y);
@@ -315,13 +333,16 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(p_full(i));
             }
-            // ---- epilogue: O / l -> bf16, token-major
+            // ---- epilogue: O / l -> bf16, token-major; the two halves first add up their row sums
+            *xslot(n_kv & 1, half) = l_sum;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
+            l_sum += *xslot(n_kv & 1, half ^ 1);
             mbar_wait(o_full(i), 0, 31);
             tc_fence_after();
             const float inv = 1.0f / l_sum;
-            __nv_bfloat16* orow = p.out + ((int64_t)b * p.L + qrow) * p.ldo + h * HD;
+            __nv_bfloat16* orow = p.out + ((int64_t)b * p.L + qrow) * p.ldo + h * HD + half * (HD / 2);
 #pragma unroll 1
-            for (int c = 0; c < HD / 32; ++c) {
+            for (int c = 0; c < HD / 64; ++c) {
                 uint32_t ov[32];
                 tmem_ld_32x32b_x32(t_o + c * 32, ov);
                 tmem_ld_wait();
@@ -342,7 +363,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc<1>(tmem, 512);
     }
