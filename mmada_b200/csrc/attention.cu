@@ -25,7 +25,7 @@
 
 namespace mmada {
 
-constexpr int ATT_THREADS = 576;   // 16 softmax warps + TMA warp + MMA warp; 576 x 112 registers fit the SM
+constexpr int ATT_THREADS = 576;   // 16 softmax warps + TMA warp + MMA warp; 20 warp slots x 96 registers
 constexpr int QT = 128;    // query rows per tile
 constexpr int KT = 128;    // keys per tile
 constexpr int TMA_WARP = 16, MMA_WARP = 17;
@@ -93,7 +93,7 @@ struct AttnCfg {
 };
 
 template <int HD>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
     using Cfg = AttnCfg<HD>;
