@@ -257,8 +257,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t t_o = tmem + Cfg::TM_O + HD * i + half * (HD / 2) + lane_off;
             const int rloc = quarter * 32 + lane;
             const int qrow = q0 + i * QT + rloc;
-            float* xchg = reinterpret_cast<float*>(smem + Cfg::XCHG_OFF);
-            auto xslot = [&](int par, int hf) { return xchg + ((par * 2 + i) * 2 + hf) * 128 + rloc; };
+            // exchange slots in shared memory (addressed in the shared window: LDS/STS, not generic loads)
+            const uint32_t xchg = sbase + Cfg::XCHG_OFF;
+            auto xslot = [&](int par, int hf) { return xchg + 4u * (uint32_t)(((par * 2 + i) * 2 + hf) * 128 + rloc); };
+            auto xst = [&](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
+            auto xld = [&](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; };
+            const int pair_bar = 1 + i * 4 + quarter;       // the two warps that share this lane quarter
             float m_used = -INFINITY, l_sum = 0.f;
             for (int j = 0; j < n_kv; ++j) {
                 const int keys = (j == n_kv - 1) ? tail : KT;          // valid keys
@@ -285,9 +289,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         mxa[t] = fmaxf(mxa[t], fmaxf(__uint_as_float(sv[c + 2 * t]), __uint_as_float(sv[c + 2 * t + 1])));
                 }
                 float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-                *xslot(j & 1, half) = mx;
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
-                mx = fmaxf(mx, *xslot(j & 1, half ^ 1));
+                xst(xslot(j & 1, half), mx);
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                mx = fmaxf(mx, xld(xslot(j & 1, half ^ 1)));
                 // lazy rescale: keep the stale reference max unless it grows by more than 2^8
                 const float m_new = fmaxf(m_used, mx);
                 const bool grow = (m_new - m_used) * p.scale_log2 > 8.0f;
@@ -311,21 +315,21 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const float mb = m_used * p.scale_log2;
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nmb2 = make_float2(-mb, -mb);
                 float2 rs2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores
+                // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores, 16 keys at a time
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (kbase + c * 32 < keys16) {
-                        uint32_t pw[16];
+                for (int c = 0; c < 4; ++c) {
+                    if (kbase + c * 16 < keys16) {
+                        uint32_t pw[8];
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
+                        for (int t = 0; t < 8; ++t) {
                             // packed fp32x2: one FFMA2 scales-and-shifts two scores, one FADD2 adds two exponentials
-                            const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 32 + 2 * t]), __uint_as_float(sv[c * 32 + 2 * t + 1])),
+                            const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 16 + 2 * t]), __uint_as_float(sv[c * 16 + 2 * t + 1])),
                                                    sc2, nmb2);
                             const float2 e = make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
                             rs2[t & 3] = fadd2(rs2[t & 3], e);
                             pw[t] = pack_bf16(e.x, e.y);
                         }
-                        tmem_st_32x32b_x16(t_s + (kbase >> 1) + c * 16, pw);
+                        tmem_st_32x32b_x8(t_s + (kbase >> 1) + c * 8, pw);
                     }
                 }
                 l_sum += (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y) + (rs2[2].x + rs2[2].y) + (rs2[3].x + rs2[3].y);
@@ -334,9 +338,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 mbar_arrive(p_full(i));
             }
             // ---- epilogue: O / l -> bf16, token-major; the two halves first add up their row sums
-            *xslot(n_kv & 1, half) = l_sum;
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
-            l_sum += *xslot(n_kv & 1, half ^ 1);
+            xst(xslot(n_kv & 1, half), l_sum);
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            l_sum += xld(xslot(n_kv & 1, half ^ 1));
             mbar_wait(o_full(i), 0, 31);
             tc_fence_after();
             const float inv = 1.0f / l_sum;
