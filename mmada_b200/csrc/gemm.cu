@@ -21,6 +21,8 @@
 // The producer and MMA warps run their loops with all 32 lanes (addresses stay warp-uniform) and
 // elect one lane only around the TMA / MMA instructions: a single diverged lane executing the loop
 // bookkeeping was measured to cap the tensor pipe at ~36 %.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mmada_b200.h"
@@ -31,7 +33,6 @@ constexpr int BK = 64;          // k-block: 64 bf16 = 128 bytes = one swizzle ro
 constexpr int BM = 128;         // A rows per CTA
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-constexpr int GROUP_M = 8;      // rasterisation: tiles walk GROUP_M m-tiles before the next n-tile
 
 struct GemmParams {
     void* out;
@@ -42,6 +43,8 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
     // convolution mode (A = NHWC activations [B,H,W,C], K = taps * C)
     int conv_H, conv_W, conv_C, conv_taps;   // taps = 9 (3x3, pad 1) or 1
+    int group_m;                             // rasterisation: tiles walk group_m m-tiles before the next n-tile
+    uint64_t hint_a, hint_b;                 // L2 eviction-priority hints of the operand loads
 };
 
 template <int CG, int BN>
@@ -56,7 +59,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGING_OFF + STAGING_BYTES + 1024 /*align*/;
 };
 
-__device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int& mt, int& nt) {
+__device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int GROUP_M, int& mt, int& nt) {
     const int per_group = GROUP_M * num_n_tiles;
     const int g = idx / per_group;
     const int first_m = g * GROUP_M;
@@ -209,7 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int mt, nt;
-            tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
             const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
             const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
             // convolution: the 128 rows are 128 consecutive NHWC pixels = a BW x BH box of one image
@@ -234,14 +237,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if constexpr (CONV) {
                         const int tap = kb / kpc, kc = kb - tap * kpc;
                         const int dy = p.conv_taps == 9 ? tap / 3 - 1 : 0, dx = p.conv_taps == 9 ? tap % 3 - 1 : 0;
-                        if constexpr (CG == 1) tma_load_4d(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb);
-                        else tma_load_4d_2sm(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb);
+                        if constexpr (CG == 1) tma_load_4d(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb, p.hint_a);
+                        else tma_load_4d_2sm(sa, &map_a, fb, kc * BK, cx + dx, cy + dy, cb, p.hint_a);
                     } else {
-                        if constexpr (CG == 1) tma_load_2d(sa, &map_a, fb, kb * BK, m0);
-                        else tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0);
+                        if constexpr (CG == 1) tma_load_2d(sa, &map_a, fb, kb * BK, m0, p.hint_a);
+                        else tma_load_2d_2sm(sa, &map_a, fb, kb * BK, m0, p.hint_a);
                     }
-                    if constexpr (CG == 1) tma_load_2d(sb, &map_b, fb, kb * BK, n0);
-                    else tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0);
+                    if constexpr (CG == 1) tma_load_2d(sb, &map_b, fb, kb * BK, n0, p.hint_b);
+                    else tma_load_2d_2sm(sb, &map_b, fb, kb * BK, n0, p.hint_b);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -293,7 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int mt, nt;
-            tile_coords(t, p.num_m_tiles, p.num_n_tiles, mt, nt);
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, mt, nt);
             const int row = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32 + lane;
             uint8_t* stage = smem + Cfg::STAGING_OFF + (warp - 2) * (32 * 144);
             const int row0 = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32;       // first row of this warp
@@ -482,6 +485,22 @@ static int dispatch_conv256(int epi, const CUtensorMap& ma, const CUtensorMap& m
 
 using namespace mmada;
 
+// rasterisation / cache-hint defaults, overridable for experiments (MMADA_GEMM_GROUP_M, MMADA_GEMM_HINTS=ab with
+// a,b in {n,f,l} = normal / evict-first / evict-last for the A and B operand loads)
+static void set_tuning(GemmParams& p) {
+    static int group_m = 0;
+    static uint64_t ha = kEvictNormal, hb = kEvictNormal;
+    if (group_m == 0) {
+        const char* g = getenv("MMADA_GEMM_GROUP_M");
+        group_m = g ? atoi(g) : 8;
+        if (group_m < 1) group_m = 8;
+        const char* h = getenv("MMADA_GEMM_HINTS");
+        auto dec = [](char c) { return c == 'f' ? kEvictFirst : (c == 'l' ? kEvictLast : kEvictNormal); };
+        if (h && h[0] && h[1]) { ha = dec(h[0]); hb = dec(h[1]); }
+    }
+    p.group_m = group_m; p.hint_a = ha; p.hint_b = hb;
+}
+
 extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
                                const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
                                void* stream) {
@@ -505,6 +524,7 @@ extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.M = M; p.N = N; p.K = K;
     p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
     p.num_n_tiles = (N + bn - 1) / bn;
+    set_tuning(p);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (narrow) return dispatch_narrow<false>(epilogue, ma, mb, p, s);
     return cta_group == 1 ? dispatch_gemm256<1>(epilogue, ma, mb, p, s) : dispatch_gemm256<2>(epilogue, ma, mb, p, s);
@@ -538,6 +558,7 @@ extern "C" int mmada_conv_nhwc_bf16(const void* in, const void* weight, const fl
     p.num_m_tiles = (p.M + 255) / 256;
     p.num_n_tiles = (C_out + bn - 1) / bn;
     p.conv_H = H; p.conv_W = W; p.conv_C = C_in; p.conv_taps = taps;
+    set_tuning(p);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     return bn == 128 ? dispatch_narrow<true>(epilogue, ma, mb, p, s) : dispatch_conv256(epilogue, ma, mb, p, s);
 }
