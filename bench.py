@@ -55,6 +55,15 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (not live)."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch_avg"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -298,7 +307,7 @@ def run_own(args):
             by[k] = (t + a.elapsed_time(b), n + 1, 2.0 * M * N * Kk)
         roof = {"bound": "tensor", "kernel": f"mmada::gemm_kernel<{args.cta_group},*> (tcgen05 UMMA 256x256x16, TMA, TMEM)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "peak_source": pk["source"] + " cuBLAS bf16 sustained", "traffic": None,
+                "peak_source": pk["source"] + " cuBLAS bf16 sustained", "traffic": _ncu_traffic(),
                 "launches": len(gemm_events), "avg_launch_ms": tot_ms / len(gemm_events),
                 "share_of_step": tot_ms / ms,
                 "per_shape": {k: {"ms": t / n, "tflops": fl / (t / n * 1e-3) / 1e12} for k, (t, n, fl) in by.items()}}
