@@ -39,11 +39,20 @@ enum {
                                   rows [256j,256j+128) = ff_proj rows [128j,..), next 128 = up_proj  */
     MMADA_EPI_BIAS_BF16 = 4,   /* out bf16 [M,N] = acc + bias fp32 [N]                               */
     MMADA_EPI_BIAS_F32 = 5,    /* out fp32 [M,N] = acc + bias                                        */
-    MMADA_EPI_BIAS_RESID_F32 = 6 /* out fp32 [M,N] = acc + bias + aux fp32 [M,N]                      */
+    MMADA_EPI_BIAS_RESID_F32 = 6, /* out fp32 [M,N] = acc + bias + aux fp32 [M,N]                     */
+    MMADA_EPI_ROPE_BF16 = 7    /* (mmada_gemm_qkv_rope_bf16 only) bf16 store with rotary embedding       */
 };
 int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
                     const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
                     void* stream);
+
+/* Fused q|k|v projection + rotary embedding: out bf16 [M,N] = A . B^T, then NeoX half-split RoPE on every
+ * head inside columns [0, rope_cols) (q and k; rope_cols = 2*d_model) with position = row % seq_len and
+ * the reference's fp32 sin/cos tables [>= seq_len, head_dim/2]; N % 256 == 0, head_dim 64 or 128.
+ * Replaces q/k/v_proj (models/modeling_llada.py:901-903) + RotaryEmbedding.forward (:411-428).     */
+int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                             const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols,
+                             int head_dim, int seq_len, int cta_group, void* stream);
 
 /* ---- HBM-bound block kernels ----------------------------------------------------------------
  * embed:   out fp32 [M,d] = table bf16 [vocab,d][ids[m]]         models/modeling_llada.py:1222

@@ -43,6 +43,9 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
     // convolution mode (A = NHWC activations [B,H,W,C], K = taps * C)
     int conv_H, conv_W, conv_C, conv_taps;   // taps = 9 (3x3, pad 1) or 1
+    const float* rope_sin;                   // MMADA_EPI_ROPE_BF16: fp32 tables [>= rope_L, rope_hd/2]
+    const float* rope_cos;
+    int rope_hd, rope_L, rope_cols;          // head dim, sequence length (position = row % L), columns [0, rope_cols) are rotated
     int group_m;                             // rasterisation: tiles walk group_m m-tiles before the next n-tile
     uint64_t hint_a, hint_b;                 // L2 eviction-priority hints of the operand loads
 };
@@ -73,7 +76,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 
 __host__ __device__ constexpr bool epi_has_bias(int e) { return e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_BIAS_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
 __host__ __device__ constexpr bool epi_has_resid(int e) { return e == MMADA_EPI_RESID_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
-__host__ __device__ constexpr bool epi_out_bf16(int e) { return e == MMADA_EPI_BF16 || e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_SWIGLU_BF16; }
+__host__ __device__ constexpr bool epi_out_bf16(int e) { return e == MMADA_EPI_BF16 || e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_SWIGLU_BF16 || e == MMADA_EPI_ROPE_BF16; }
 
 // one 32-column chunk of one accumulator row
 template <int EPI>
@@ -155,6 +158,36 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, 
         }
     }
     __syncwarp();
+}
+
+// NeoX half-split rotary embedding of one head segment held by a thread: lo/hi = the two halves (HALF fp32
+// accumulators each) of one head of one token row.  Mirrors the reference's order of operations
+// (models/modeling_llada.py:402-428): the projection output is first rounded to the model dtype (bf16), the
+// rotation is evaluated in fp32 as t*cos + rotate_half(t)*sin with separately rounded products, and the result is
+// rounded to bf16 again.  In place: afterwards lo[0..HALF/2) / hi[0..HALF/2) hold the packed bf16 pairs of the halves.
+template <int HALF>
+__device__ __forceinline__ void rope_pack(uint32_t* lo, uint32_t* hi, const float* sn, const float* cs, bool rotate) {
+#pragma unroll
+    for (int j = 0; j < HALF; j += 4) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rotate) {
+            s4 = __ldg(reinterpret_cast<const float4*>(sn + j));
+            c4 = __ldg(reinterpret_cast<const float4*>(cs + j));
+        }
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, c[4] = {c4.x, c4.y, c4.z, c4.w};
+        float ol[4], oh[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float l = __bfloat162float(__float2bfloat16_rn(__uint_as_float(lo[j + t])));
+            const float h = __bfloat162float(__float2bfloat16_rn(__uint_as_float(hi[j + t])));
+            ol[t] = rotate ? __fadd_rn(__fmul_rn(l, c[t]), __fmul_rn(-h, s[t])) : l;
+            oh[t] = rotate ? __fadd_rn(__fmul_rn(h, c[t]), __fmul_rn(l, s[t])) : h;
+        }
+        lo[j / 2] = pack_bf16(ol[0], ol[1]);          // slots j/2, j/2+1 <= j: already consumed
+        lo[j / 2 + 1] = pack_bf16(ol[2], ol[3]);
+        hi[j / 2] = pack_bf16(oh[0], oh[1]);
+        hi[j / 2 + 1] = pack_bf16(oh[2], oh[3]);
+    }
 }
 
 template <int CG, int EPI, int BN, bool CONV>
@@ -341,6 +374,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                          silu_f(__uint_as_float(g[2 * j + 1])) * __uint_as_float(u[2 * j + 1]));
                     if (rows_valid > 0) staged_store<64, false>(stage, w, obase + c * 64, nullptr, pitch, rows_valid, lane);
                 }
+            } else if constexpr (EPI == MMADA_EPI_ROPE_BF16) {
+                // fused q|k|v projection: heads inside columns [0, rope_cols) are rotated before the store
+                const int pos = (row < p.M ? row : 0) % p.rope_L;
+                uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch;
+                if (p.rope_hd == 128) {
+                    const float* sn = p.rope_sin + (int64_t)pos * 64;
+                    const float* cs = p.rope_cos + (int64_t)pos * 64;
+#pragma unroll 1
+                    for (int hh = 0; hh < BN / 128; ++hh) {
+                        const int col0 = nt * BN + hh * 128;
+                        uint32_t lo[64], hi[64];
+                        tmem_ld_32x32b_x32(t_addr + hh * 128, lo);
+                        tmem_ld_32x32b_x32(t_addr + hh * 128 + 32, lo + 32);
+                        tmem_ld_32x32b_x32(t_addr + hh * 128 + 64, hi);
+                        tmem_ld_32x32b_x32(t_addr + hh * 128 + 96, hi + 32);
+                        tmem_ld_wait();
+                        rope_pack<64>(lo, hi, sn, cs, col0 < p.rope_cols);
+                        if (rows_valid > 0) {
+                            staged_store<128, false>(stage, lo, obase + (int64_t)col0 * 2, nullptr, pitch, rows_valid, lane);
+                            staged_store<128, false>(stage, hi, obase + (int64_t)col0 * 2 + 128, nullptr, pitch, rows_valid, lane);
+                        }
+                    }
+                } else {   // head_dim 64
+                    const float* sn = p.rope_sin + (int64_t)pos * 32;
+                    const float* cs = p.rope_cos + (int64_t)pos * 32;
+#pragma unroll 1
+                    for (int hh = 0; hh < BN / 64; ++hh) {
+                        const int col0 = nt * BN + hh * 64;
+                        uint32_t lo[32], hi[32];
+                        tmem_ld_32x32b_x32(t_addr + hh * 64, lo);
+                        tmem_ld_32x32b_x32(t_addr + hh * 64 + 32, hi);
+                        tmem_ld_wait();
+                        rope_pack<32>(lo, hi, sn, cs, col0 < p.rope_cols);
+                        if (rows_valid > 0) {   // 64 bytes (low half) then 64 bytes (high half) of the 128-byte head
+                            staged_store<64, false>(stage, lo, obase + (int64_t)col0 * 2, nullptr, pitch, rows_valid, lane);
+                            staged_store<64, false>(stage, hi, obase + (int64_t)col0 * 2 + 64, nullptr, pitch, rows_valid, lane);
+                        }
+                    }
+                }
             } else if constexpr (epi_out_bf16(EPI)) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
@@ -457,6 +529,7 @@ static int dispatch_gemm256(int epi, const CUtensorMap& ma, const CUtensorMap& m
         case MMADA_EPI_BIAS_BF16: return launch_gemm<CG, MMADA_EPI_BIAS_BF16, 256, false>(ma, mb, p, s);
         case MMADA_EPI_BIAS_F32: return launch_gemm<CG, MMADA_EPI_BIAS_F32, 256, false>(ma, mb, p, s);
         case MMADA_EPI_BIAS_RESID_F32: return launch_gemm<CG, MMADA_EPI_BIAS_RESID_F32, 256, false>(ma, mb, p, s);
+        case MMADA_EPI_ROPE_BF16: return launch_gemm<CG, MMADA_EPI_ROPE_BF16, 256, false>(ma, mb, p, s);
     }
     return kBadArgument;
 }
@@ -489,11 +562,11 @@ using namespace mmada;
 // a,b in {n,f,l} = normal / evict-first / evict-last for the A and B operand loads)
 static void set_tuning(GemmParams& p) {
     static int group_m = 0;
-    static uint64_t ha = kEvictNormal, hb = kEvictNormal;
+    static uint64_t ha = kEvictLast, hb = kEvictNormal;   // measured: +2 % sustained vs (8, normal/normal)
     if (group_m == 0) {
         const char* g = getenv("MMADA_GEMM_GROUP_M");
-        group_m = g ? atoi(g) : 8;
-        if (group_m < 1) group_m = 8;
+        group_m = g ? atoi(g) : 16;
+        if (group_m < 1) group_m = 16;
         const char* h = getenv("MMADA_GEMM_HINTS");
         auto dec = [](char c) { return c == 'f' ? kEvictFirst : (c == 'l' ? kEvictLast : kEvictNormal); };
         if (h && h[0] && h[1]) { ha = dec(h[0]); hb = dec(h[1]); }
@@ -507,7 +580,7 @@ extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return kBadArgument;
     if ((lda % 8) || (ldb % 8) || (K % 8)) return kUnsupportedShape;        // 16-byte global strides for TMA
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return kBadArgument;
-    if (epilogue < 0 || epilogue > MMADA_EPI_BIAS_RESID_F32) return kBadArgument;
+    if (epilogue < 0 || epilogue > MMADA_EPI_BIAS_RESID_F32) return kBadArgument;     // ROPE has its own entry point
     if (epilogue == MMADA_EPI_SWIGLU_BF16 && (N % 256)) return kUnsupportedShape;
     if (epi_has_resid(epilogue) && !aux) return kBadArgument;
     if (epi_has_bias(epilogue) && !bias) return kBadArgument;
@@ -528,6 +601,35 @@ extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (narrow) return dispatch_narrow<false>(epilogue, ma, mb, p, s);
     return cta_group == 1 ? dispatch_gemm256<1>(epilogue, ma, mb, p, s) : dispatch_gemm256<2>(epilogue, ma, mb, p, s);
+}
+
+// Fused q|k|v projection + rotary embedding: out bf16 [M, N] = A . B^T with RoPE applied to the heads inside
+// columns [0, rope_cols) (q and k), position = row % seq_len.
+extern "C" int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                                        const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols,
+                                        int head_dim, int seq_len, int cta_group, void* stream) {
+    if (!A || !B || !out || !sin_table || !cos_table || M <= 0 || N <= 0 || K <= 0 || seq_len <= 0) return kBadArgument;
+    if ((lda % 8) || (ldb % 8) || (K % 8) || (ldo % 8) || (N % 256)) return kUnsupportedShape;
+    if ((head_dim != 64 && head_dim != 128) || rope_cols % head_dim || rope_cols > N) return kUnsupportedShape;
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(out) |
+         reinterpret_cast<uintptr_t>(sin_table) | reinterpret_cast<uintptr_t>(cos_table)) & 15)
+        return kBadArgument;
+    if (cta_group != 1 && cta_group != 2) return kBadArgument;
+    CUtensorMap ma, mb;
+    int st = make_tmap_bf16_2d(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM);
+    if (st) return st;
+    st = make_tmap_bf16_2d(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(256 / cta_group));
+    if (st) return st;
+    GemmParams p = {};
+    p.out = out; p.ldo = ldo;
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
+    p.num_n_tiles = N / 256;
+    p.rope_sin = sin_table; p.rope_cos = cos_table; p.rope_hd = head_dim; p.rope_L = seq_len; p.rope_cols = rope_cols;
+    set_tuning(p);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return cta_group == 1 ? dispatch_gemm256<1>(MMADA_EPI_ROPE_BF16, ma, mb, p, s)
+                          : dispatch_gemm256<2>(MMADA_EPI_ROPE_BF16, ma, mb, p, s);
 }
 
 // NHWC convolution as an implicit GEMM: out[b,y,x,co] = bias[co] + sum_{tap,c} in[b,y+dy,x+dx,c] * w[co,tap,c] (+ resid)

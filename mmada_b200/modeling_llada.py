@@ -84,6 +84,8 @@ class LLaDAModelLM:
         self.head: Optional[torch.Tensor] = None
         self._rope = None
         self.cta_group = 2
+        #: RoPE in the epilogue of the fused q|k|v GEMM (needs 3*d_model % 256 == 0 and head_dim in {64, 128})
+        self.fused_rope = (3 * config.d_model) % 256 == 0 and config.head_dim in (64, 128)
         self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
 
     # ---- weights ---------------------------------------------------------------------------
@@ -158,14 +160,17 @@ class LLaDAModelLM:
         cg = self.cta_group
         for ly in self.layers:
             ops.rmsnorm(x, ly.attn_norm, c.rms_norm_eps, out=xn)
-            ops.gemm(xn, ly.wqkv, ops.EPI_BF16, out=qkv, cta_group=cg)
-            ops.rope_inplace(qkv, sin, cos, c.d_model, c.head_dim, L)
+            if self.fused_rope:
+                ops.gemm_qkv_rope(xn, ly.wqkv, sin, cos, c.d_model, c.head_dim, L, out=qkv, cta_group=cg)
+            else:
+                ops.gemm(xn, ly.wqkv, ops.EPI_BF16, out=qkv, cta_group=cg)
+                ops.rope_inplace(qkv, sin, cos, c.d_model, c.head_dim, L)
             ops.attention(qkv, B, L, c.n_heads, c.head_dim, out=att)
             ops.gemm(att, ly.attn_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
             ops.rmsnorm(x, ly.ff_norm, c.rms_norm_eps, out=xn)
             ops.gemm(xn, ly.w_gate_up, ops.EPI_SWIGLU_BF16, out=h, cta_group=cg)
             ops.gemm(h, ly.ff_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
-        self.kernel_launches += 1 + 8 * len(self.layers)
+        self.kernel_launches += 1 + (7 if self.fused_rope else 8) * len(self.layers)
         return x
 
     @torch.no_grad()

@@ -61,6 +61,28 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Option
     return out
 
 
+def gemm_qkv_rope(a: torch.Tensor, wqkv: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, d_model: int, head_dim: int,
+                  seq_len: int, out: Optional[torch.Tensor] = None, cta_group: int = 2) -> torch.Tensor:
+    """Fused q|k|v projection + RoPE on the q and k thirds (see mmada_gemm_qkv_rope_bf16)."""
+    _chk(a, torch.bfloat16, "a"); _chk(wqkv, torch.bfloat16, "wqkv"); _chk(sin, torch.float32, "sin"); _chk(cos, torch.float32, "cos")
+    M, K = a.shape
+    N = wqkv.shape[0]
+    assert a.stride(1) == 1 and wqkv.stride(1) == 1 and sin.is_contiguous() and cos.is_contiguous()
+    assert sin.shape[-1] == head_dim // 2 and sin.shape[0] >= seq_len
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    ev = GEMM_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.call("mmada_gemm_qkv_rope_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0), out.data_ptr(),
+              out.stride(0), sin.data_ptr(), cos.data_ptr(), M, N, K, 2 * d_model, head_dim, seq_len, cta_group, _stream())
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1, M, N, K, 7))
+    return out
+
+
 def embed(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     _chk(ids, torch.int64, "ids"); _chk(table, torch.bfloat16, "table")
     ids = ids.contiguous().view(-1)

@@ -100,6 +100,25 @@ def test_rope(hd, H):
     assert torch.equal(qkv[:, 2 * d:], v0)
 
 
+@pytest.mark.parametrize("hd,H,L,B", [(64, 4, 77, 3), (128, 4, 100, 2), (128, 2, 387, 2)])
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_qkv_rope_fused_equals_unfused(hd, H, L, B, cta_group):
+    """RoPE in the q|k|v GEMM epilogue == bf16 GEMM followed by the stand-alone RoPE kernel, bit for bit
+    (same rounding points: bf16 projection output, fp32 rotation, bf16 result)."""
+    from mmada_b200 import ops
+    from oracle import llada
+    d = H * hd
+    g = torch.Generator(device="cuda").manual_seed(hd + L)
+    a = torch.randn(B * L, d, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * d, d, device="cuda", generator=g) / math.sqrt(d)).bfloat16()
+    sin, cos = llada.rope_tables(L, hd, 500000.0)
+    sin_h, cos_h = sin[0, 0, :, :hd // 2].contiguous().cuda(), cos[0, 0, :, :hd // 2].contiguous().cuda()
+    ref = ops.gemm(a, w, ops.EPI_BF16, cta_group=cta_group)
+    ops.rope_inplace(ref, sin_h, cos_h, d, hd, L)
+    out = ops.gemm_qkv_rope(a, w, sin_h, cos_h, d, hd, L, cta_group=cta_group)
+    assert torch.equal(out, ref)
+
+
 def test_embed():
     from mmada_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)
