@@ -68,12 +68,25 @@ def load() -> C.CDLL:
     return _lib
 
 
+#: profiling hook: when set to a list, every kernel call appends (name, start_event, end_event) recorded on
+#: torch's current stream (scripts/bench_step_breakdown.py)
+EVENTS = None
+
+
 def call(name: str, *args) -> None:
     lib = load()
     fn = getattr(lib, name, None)
     if fn is None:
         raise MMadaKernelError(f"{name} is not exported by {LIB_PATH}")
-    st = fn(*args)
+    if EVENTS is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = fn(*args)
+        e1.record()
+        EVENTS.append((name, e0, e1))
+    else:
+        st = fn(*args)
     if st != 0:
         detail = ""
         if st >= 1000:
