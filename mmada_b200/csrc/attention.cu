@@ -7,75 +7,60 @@
 // q, k, v are read in place from the fused projection output [B*L, ld] (head h at columns h*hd),
 // the output is written token-major [B*L, ldo] ready for the attn_out GEMM: no transposes.
 //
-// One CTA handles one (batch, head) and up to two 128-row query tiles ("ping-pong"):
-//   warps 0-3 / 4-7  softmax for query tile 0 / 1, one thread per query row: tcgen05.ld the 128
-//                    scores of the row, online softmax in base 2 with lazy rescaling of the output
-//                    accumulator (only when the running max grows by more than 2^8), write P (bf16)
-//                    back into the TMEM columns the scores came from
+// One CTA handles one (batch, head) and up to two 128-row query tiles.  Keys are consumed in SUB-TILES of
+// 64: every query tile owns two 64-column score buffers in TMEM, so the tensor pipe computes the scores
+// of sub-tile t+1 (and t+2) while the softmax threads still work on sub-tile t.  With 128-key score tiles
+// (one buffer per query tile) the chain  S -> softmax -> P -> PV -> next S  was serial per query tile and
+// the kernel sat at 40 % tensor-pipe (profiles/r01_attention_*); the double buffer makes it a throughput
+// problem (MUFU / issue slots / tensor pipe) instead of a latency problem.
+//   warps 0-3 / 4-7  softmax for query tile 0 / 1, ONE thread per query row (no cross-thread exchange):
+//                    tcgen05.ld the 64 scores, online softmax in base 2 with lazy rescaling of the output
+//                    accumulator (only when the running max grows by more than 2^8), P (bf16) written back
+//                    over the first 32 columns of the score buffer.  A compile-time share of the
+//                    exponentials runs as a polynomial on the FMA pipe (the MUFU pipe, 16 ex2/clk/SM, needs
+//                    as long for a 128x128 tile as the tensor pipe needs for its two MMAs).
 //   warp 8           TMA producer: Q once, then K/V tiles of 128 keys through 2-stage rings
-//   warp 9           MMA issuer: S_i = Q_i K^T (both operands K-major in shared memory) and
-//                    O_i += P_i V (P from TMEM, V as an MN-major shared-memory operand)
-// TMEM: S0 | S1 | O0 | O1  (128 + 128 + hd + hd columns).  While one tile's softmax runs, the tensor
-// pipe works on the other tile.  The last key tile is shortened to a multiple of 16 keys.
+//   warp 9           MMA issuer: S_i(t) = Q_i K_t^T (both operands K-major in shared memory, N = 64) and
+//                    O_i += P_i(t) V_t (P from TMEM, V as an MN-major shared-memory operand)
+// TMEM: S0a S0b | S1a S1b | O0 | O1  (4 x 64 + 2 x hd columns).  The last sub-tile is shortened to a
+// multiple of 16 keys.
 #include <math.h>
+#include <stdlib.h>
 
+#include "attn_math.cuh"
 #include "common.cuh"
 #include "host_utils.h"
 #include "../../include/mmada_b200.h"
 
 namespace mmada {
 
-constexpr int ATT_THREADS = 576;   // 16 softmax warps + TMA warp + MMA warp; 20 warp slots x 96 registers
+constexpr int ATT_THREADS = 320;   // 8 softmax warps + TMA warp + MMA warp
 constexpr int QT = 128;    // query rows per tile
-constexpr int KT = 128;    // keys per tile
-constexpr int TMA_WARP = 16, MMA_WARP = 17;
+constexpr int KT = 128;    // keys per TMA tile
+constexpr int KS = 64;     // keys per score sub-tile
+constexpr int TMA_WARP = 8, MMA_WARP = 9;
+constexpr int kAttnPolyDefault = 2;
 
 struct AttnParams {
     __nv_bfloat16* out;
     int64_t ldo;
     int L, H, B;
     float scale_log2;      // softmax scale * log2(e)
+#ifdef MMADA_ATT_TRACE
+    long long* trace;      // debug build only: clock64 timeline of CTA 0 (scripts/attn_trace.py)
+#endif
 };
 
-// 2^x on the MUFU pipe (one instruction; flush-to-zero, -inf -> 0)
-__device__ __forceinline__ float ex2_mufu(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// 2^x on the FMA pipe: floor via the 1.5*2^23 magic add (round-down), degree-3 minimax polynomial of 2^f on
-// [0,1), exponent patched in with an integer add.  Relative error ~1e-4 — P is rounded to bf16 (2^-9) anyway.
-// Part of every row goes through here so that the MUFU pipe (16 ex2/clk/SM) is not the softmax bottleneck.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float r = __fadd_rd(x, 12582912.0f);
-    const float f = x - (r - 12582912.0f);
-    float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
-    p = fmaf(p, f, 0.695146143436431885f);
-    p = fmaf(p, f, 1.0f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
-}
-
-// packed fp32x2 arithmetic (sm_100): two lanes per instruction
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    uint64_t ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    uint64_t ra, rb, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
+#ifdef MMADA_ATT_TRACE
+// slot layout: [role 0..2][t 0..63][event 0..7]
+#define ATT_TR(role, t, ev)                                                                   \
+    do {                                                                                        \
+        if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 64)                  \
+            p.trace[((role) * 64 + (t)) * 8 + (ev)] = clock64();                                \
+    } while (0)
+#else
+#define ATT_TR(role, t, ev) do {} while (0)
+#endif
 
 template <int HD>
 struct AttnCfg {
@@ -86,13 +71,13 @@ struct AttnCfg {
     static constexpr int K_OFF = 2 * TILE_BYTES;            // 2 stages
     static constexpr int V_OFF = 4 * TILE_BYTES;            // 2 stages
     static constexpr int BAR_OFF = 6 * TILE_BYTES;
-    static constexpr int XCHG_OFF = BAR_OFF + 256;          // float [2 parity][2 tiles][2 halves][128 rows]
-    static constexpr int SMEM_BYTES = XCHG_OFF + 2 * 2 * 2 * 128 * 4 + 1024;
-    static constexpr int TM_S = 0;                          // S_i at TM_S + 128 i
+    static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+    static constexpr int TM_S = 0;                          // S_i buffer b at TM_S + 128 i + 64 b
     static constexpr int TM_O = 256;                        // O_i at TM_O + HD i
 };
 
-template <int HD>
+// POLY = how many of the 8 key pairs of every 16-key chunk take the polynomial instead of MUFU.EX2
+template <int HD, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
@@ -101,17 +86,19 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + Cfg::BAR_OFF;
-    // barriers: q_full | k_full[2] | k_empty[2] | v_full[2] | v_empty[2] | s_full[2] | p_full[2] | o_full[2] | tmem ptr
+    // barriers: q_full | k_full[2] | k_empty[2] | v_full[2] | v_empty[2] | s_full[2][2] | p_full[2][2] |
+    //           pv_done[2][2] | o_full[2] | tmem ptr
     const uint32_t q_full = bars;
     auto k_full = [&](int s) { return bars + 8 * (1 + s); };
     auto k_empty = [&](int s) { return bars + 8 * (3 + s); };
     auto v_full = [&](int s) { return bars + 8 * (5 + s); };
     auto v_empty = [&](int s) { return bars + 8 * (7 + s); };
-    auto s_full = [&](int i) { return bars + 8 * (9 + i); };
-    auto p_full = [&](int i) { return bars + 8 * (11 + i); };
-    auto o_full = [&](int i) { return bars + 8 * (13 + i); };
-    const uint32_t tmem_ptr_addr = bars + 8 * 15;
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * 15);
+    auto s_full = [&](int i, int b) { return bars + 8 * (9 + 2 * i + b); };
+    auto p_full = [&](int i, int b) { return bars + 8 * (13 + 2 * i + b); };
+    auto pv_done = [&](int i, int b) { return bars + 8 * (17 + 2 * i + b); };
+    auto o_full = [&](int i) { return bars + 8 * (21 + i); };
+    const uint32_t tmem_ptr_addr = bars + 8 * 23;
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * 23);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_pairs = (p.L + 2 * QT - 1) / (2 * QT);
@@ -120,8 +107,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int h = bh % p.H, b = bh / p.H;
     const int q0 = qp * 2 * QT;
     const int n_qt = (q0 + QT < p.L) ? 2 : 1;               // second query tile entirely out of range?
-    const int n_kv = (p.L + KT - 1) / KT;
-    const int tail = p.L - (n_kv - 1) * KT;                 // valid keys in the last tile (1..128)
+    const int n_kv = (p.L + KT - 1) / KT;                   // TMA tiles
+    const int T = (p.L + KS - 1) / KS;                      // score sub-tiles
+    const int tail = p.L - (T - 1) * KS;                    // valid keys in the last sub-tile (1..64)
     const int tail16 = (tail + 15) & ~15;
 
     if (warp == TMA_WARP && lane == 0) {
@@ -134,9 +122,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_init(k_empty(s), 1);
             mbar_init(v_full(s), 1);
             mbar_init(v_empty(s), 1);
-            mbar_init(s_full(s), 1);
-            mbar_init(p_full(s), 256);
             mbar_init(o_full(s), 1);
+            for (int bb = 0; bb < 2; ++bb) {
+                mbar_init(s_full(s, bb), 1);
+                mbar_init(p_full(s, bb), 128);
+                mbar_init(pv_done(s, bb), 1);
+            }
         }
         fence_mbar_init();
     }
@@ -149,8 +140,6 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
 
-    // register re-balancing (setmaxnreg works per warpgroup): the 4 softmax warpgroups take what the
-    // TMA / MMA warpgroup does not need
     if (warp == TMA_WARP) {
         // ======================================= TMA producer =======================================
         // the whole warp walks the loop (uniform addresses), one elected lane issues
@@ -187,178 +176,180 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // the whole warp walks the schedule and waits; one elected lane issues MMAs and commits
         const uint64_t kdesc_hi = umma_desc_kmajor_sw128(0);
         const uint64_t vdesc_hi = umma_desc_mnmajor_sw128(0, Cfg::BOX_BYTES);
-        // S_i(j) = Q_i . K_j^T : M=128, N=keys of the tile, K=HD, both operands K-major
-        auto issue_s = [&](int i, int j) {
-            const int keys = (j == n_kv - 1) ? tail16 : KT;
+        // S_i(t) = Q_i . K_t^T : M=128, N=keys of the sub-tile, K=HD, both operands K-major.  Sub-tile t is
+        // rows [64 (t&1), +64) of TMA tile t>>1: 64 rows x 128 B = 8 swizzle atoms further on.
+        auto issue_s = [&](int i, int t) {
+            const int keys = (t == T - 1) ? tail16 : KS;
             const uint32_t idesc = umma_idesc_bf16(QT, keys);
             const uint32_t qa = (sbase + Cfg::Q_OFF + i * Cfg::TILE_BYTES) >> 4;
-            const uint32_t ka = (sbase + Cfg::K_OFF + (j & 1) * Cfg::TILE_BYTES) >> 4;
+            const uint32_t ka = (sbase + Cfg::K_OFF + ((t >> 1) & 1) * Cfg::TILE_BYTES + (t & 1) * (KS * 128)) >> 4;
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) {
                 const uint32_t off = ((k >> 2) * Cfg::BOX_BYTES + (k & 3) * 32) >> 4;
-                umma_bf16_ss<1>(tmem + Cfg::TM_S + 128 * i, kdesc_hi | (uint64_t)(qa + off), kdesc_hi | (uint64_t)(ka + off),
-                                idesc, k != 0);
+                umma_bf16_ss<1>(tmem + Cfg::TM_S + 128 * i + KS * (t & 1), kdesc_hi | (uint64_t)(qa + off),
+                                kdesc_hi | (uint64_t)(ka + off), idesc, k != 0);
             }
         };
-        // O_i += P_i(j) . V_j : M=128, N=HD, K=keys; A = P in TMEM (bf16 pairs), B = V MN-major
-        auto issue_pv = [&](int i, int j) {
-            const int keys = (j == n_kv - 1) ? tail16 : KT;
+        // O_i += P_i(t) . V_t : M=128, N=HD, K=keys; A = P in TMEM (bf16 pairs), B = V MN-major
+        auto issue_pv = [&](int i, int t) {
+            const int keys = (t == T - 1) ? tail16 : KS;
             constexpr uint32_t idesc = umma_idesc_bf16(QT, HD, 0, 1);
-            const uint32_t va = (sbase + Cfg::V_OFF + (j & 1) * Cfg::TILE_BYTES) >> 4;
+            const uint32_t va = (sbase + Cfg::V_OFF + ((t >> 1) & 1) * Cfg::TILE_BYTES + (t & 1) * (KS * 128)) >> 4;
             for (int k = 0; k < keys / 16; ++k)
-                umma_bf16_ts(tmem + Cfg::TM_O + HD * i, tmem + Cfg::TM_S + 128 * i + 8 * k,
-                             vdesc_hi | (uint64_t)(va + k * (2048 >> 4)), idesc, (j | k) != 0);
+                umma_bf16_ts(tmem + Cfg::TM_O + HD * i, tmem + Cfg::TM_S + 128 * i + KS * (t & 1) + 8 * k,
+                             vdesc_hi | (uint64_t)(va + k * (2048 >> 4)), idesc, (t | k) != 0);
         };
+        // a K (V) stage is free once the last S (PV) of its second sub-tile — or of the very last sub-tile — retires
+        auto last_of_tile = [&](int t) { return (t & 1) || t == T - 1; };
         mbar_wait(q_full, 0, 20);
         mbar_wait(k_full(0), 0, 21);
         tc_fence_after();
         if (elect_one()) {
-            for (int i = 0; i < n_qt; ++i) {
-                issue_s(i, 0);
-                umma_commit(s_full(i));
+            for (int t = 0; t < 2 && t < T; ++t) {
+                for (int i = 0; i < n_qt; ++i) {
+                    issue_s(i, t);
+                    umma_commit(s_full(i, t));
+                }
+                if (last_of_tile(t)) umma_commit(k_empty(0));
             }
-            umma_commit(k_empty(0));
         }
         __syncwarp();
-        for (int j = 0; j < n_kv; ++j) {
-            const bool more = j + 1 < n_kv;
-            mbar_wait(v_full(j & 1), (j >> 1) & 1, 22);
-            if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1, 23);
+        for (int t = 0; t < T; ++t) {
+            const int j = t >> 1, bb = t & 1;
+            const bool more = t + 2 < T;
+            if (bb == 0) {
+                mbar_wait(v_full(j & 1), (j >> 1) & 1, 22);
+                if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1, 23);
+            }
             for (int i = 0; i < n_qt; ++i) {
-                mbar_wait(p_full(i), j & 1, 24);
+                ATT_TR(2, t, 4 * i + 0);
+                mbar_wait(p_full(i, bb), j & 1, 24);
                 tc_fence_after();
+                ATT_TR(2, t, 4 * i + 1);
                 if (elect_one()) {
-                    issue_pv(i, j);
-                    if (i == n_qt - 1) umma_commit(v_empty(j & 1));
+                    issue_pv(i, t);
+                    umma_commit(pv_done(i, bb));
+                    if (i == n_qt - 1 && last_of_tile(t)) umma_commit(v_empty(j & 1));
                     if (more) {
-                        issue_s(i, j + 1);
-                        umma_commit(s_full(i));
-                        if (i == n_qt - 1) umma_commit(k_empty((j + 1) & 1));
-                    } else {
-                        umma_commit(o_full(i));
+                        issue_s(i, t + 2);
+                        umma_commit(s_full(i, bb));
+                        if (i == n_qt - 1 && last_of_tile(t + 2)) umma_commit(k_empty((j + 1) & 1));
                     }
+                    if (t == T - 1) umma_commit(o_full(i));
                 }
                 __syncwarp();
+                ATT_TR(2, t, 4 * i + 2);
             }
         }
     } else {
         // ======================================= softmax =======================================
-        // 256 threads per query tile: the row's 128 scores are split between two threads (two warps on the
-        // same TMEM lane quarter), each owning 64 key columns and half of the output columns.  The halves
-        // exchange their row maxima through shared memory once per tile (one 256-thread named barrier) and
-        // their row sums once at the end.  A single thread per row was measured latency-bound (~3000 cycles
-        // of dependent instructions per tile against 1024 cycles of MMA).
-        const int i = warp >> 3;                        // query tile
-        const int half = (warp >> 2) & 1;               // which 64 keys / which half of the head dim
-        const int quarter = warp & 3;
+        const int i = warp >> 2;                        // query tile
+        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
         if (i < n_qt) {
             const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
             const uint32_t t_s = tmem + Cfg::TM_S + 128 * i + lane_off;
-            const uint32_t t_o = tmem + Cfg::TM_O + HD * i + half * (HD / 2) + lane_off;
-            const int rloc = quarter * 32 + lane;
-            const int qrow = q0 + i * QT + rloc;
-            // exchange slots in shared memory (addressed in the shared window: LDS/STS, not generic loads)
-            const uint32_t xchg = sbase + Cfg::XCHG_OFF;
-            auto xslot = [&](int par, int hf) { return xchg + 4u * (uint32_t)(((par * 2 + i) * 2 + hf) * 128 + rloc); };
-            auto xst = [&](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
-            auto xld = [&](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; };
-            const int pair_bar = 1 + i * 4 + quarter;       // the two warps that share this lane quarter
+            const uint32_t t_o = tmem + Cfg::TM_O + HD * i + lane_off;
+            const int qrow = q0 + i * QT + quarter * 32 + lane;
             float m_used = -INFINITY, l_sum = 0.f;
-            for (int j = 0; j < n_kv; ++j) {
-                const int keys = (j == n_kv - 1) ? tail : KT;          // valid keys
+            for (int t = 0; t < T; ++t) {
+                const int bb = t & 1;
+                const int keys = (t == T - 1) ? tail : KS;              // valid keys
                 const int keys16 = (keys + 15) & ~15;
-                const int kbase = 64 * half;                            // first key of this thread's half
-                mbar_wait(s_full(i), j & 1, 30);
+                if (quarter == 0) ATT_TR(i, t, 0);
+                mbar_wait(s_full(i, bb), (t >> 1) & 1, 30);
                 tc_fence_after();
+                if (quarter == 0) ATT_TR(i, t, 1);
                 uint32_t sv[64];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (kbase + c * 32 < keys16) tmem_ld_32x32b_x32(t_s + kbase + c * 32, &sv[c * 32]);
-                }
+                tmem_ld_32x32b_x32(t_s + KS * bb, &sv[0]);
+                if (keys16 > 32) tmem_ld_32x32b_x32(t_s + KS * bb + 32, &sv[32]);
                 tmem_ld_wait();
-                if (keys < KT) {
+                if (quarter == 0) ATT_TR(i, t, 2);
+                if (keys < KS) {
 #pragma unroll
                     for (int c = 0; c < 64; ++c)
-                        if (kbase + c >= keys) sv[c] = 0xff800000u;   // -inf: masked (or never written) key
+                        if (c >= keys) sv[c] = 0xff800000u;            // -inf: masked (or never written) key
                 }
                 float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // 4 independent chains
 #pragma unroll
                 for (int c = 0; c < 64; c += 8) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        mxa[t] = fmaxf(mxa[t], fmaxf(__uint_as_float(sv[c + 2 * t]), __uint_as_float(sv[c + 2 * t + 1])));
+                    for (int u = 0; u < 4; ++u)
+                        mxa[u] = fmaxf(mxa[u], fmaxf(__uint_as_float(sv[c + 2 * u]), __uint_as_float(sv[c + 2 * u + 1])));
                 }
-                float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-                xst(xslot(j & 1, half), mx);
-                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                mx = fmaxf(mx, xld(xslot(j & 1, half ^ 1)));
+                const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
                 // lazy rescale: keep the stale reference max unless it grows by more than 2^8
                 const float m_new = fmaxf(m_used, mx);
                 const bool grow = (m_new - m_used) * p.scale_log2 > 8.0f;
-                if (j == 0) {
+                if (t == 0) {
                     m_used = m_new;
                 } else if (__any_sync(0xffffffffu, grow)) {
+                    // O_i must be quiescent: PV_i(t-1) may still be in flight
+                    mbar_wait(pv_done(i, bb ^ 1), ((t - 1) >> 1) & 1, 32);
+                    tc_fence_after();
                     const float alpha = grow ? ex2_mufu((m_used - m_new) * p.scale_log2) : 1.0f;
                     if (grow) m_used = m_new;
                     l_sum *= alpha;
 #pragma unroll 1
-                    for (int c = 0; c < HD / 32; ++c) {                 // this thread's half of the output columns
+                    for (int c = 0; c < HD / 16; ++c) {
                         uint32_t ov[16];
                         tmem_ld_32x32b_x16(t_o + c * 16, ov);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) ov[t] = __float_as_uint(__uint_as_float(ov[t]) * alpha);
+                        for (int u = 0; u < 16; ++u) ov[u] = __float_as_uint(__uint_as_float(ov[u]) * alpha);
                         tmem_st_32x32b_x16(t_o + c * 16, ov);
                     }
                     tmem_st_wait();
                 }
+                if (quarter == 0) ATT_TR(i, t, 3);
                 const float mb = m_used * p.scale_log2;
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nmb2 = make_float2(-mb, -mb);
                 float2 rs2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                // P column t holds the bf16 pair for keys (2t, 2t+1); written over the scores, 16 keys at a time
+                // P column u holds the bf16 pair for keys (2u, 2u+1); written over the scores, 16 keys at a time
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    if (kbase + c * 16 < keys16) {
+                    if (c * 16 < keys16) {
                         uint32_t pw[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
+                        for (int u = 0; u < 8; ++u) {
                             // packed fp32x2: one FFMA2 scales-and-shifts two scores, one FADD2 adds two exponentials
-                            const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 16 + 2 * t]), __uint_as_float(sv[c * 16 + 2 * t + 1])),
+                            const float2 x = ffma2(make_float2(__uint_as_float(sv[c * 16 + 2 * u]), __uint_as_float(sv[c * 16 + 2 * u + 1])),
                                                    sc2, nmb2);
-                            const float2 e = make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
-                            rs2[t & 3] = fadd2(rs2[t & 3], e);
-                            pw[t] = pack_bf16(e.x, e.y);
+                            // spread the polynomial pairs evenly through the chunk
+                            const bool poly = POLY > 0 && ((u + 1) * POLY / 8 != u * POLY / 8);
+                            const float2 e = poly ? ex2_poly2(x) : make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
+                            rs2[u & 3] = fadd2(rs2[u & 3], e);
+                            pw[u] = pack_bf16(e.x, e.y);
                         }
-                        tmem_st_32x32b_x8(t_s + (kbase >> 1) + c * 8, pw);
+                        tmem_st_32x32b_x8(t_s + KS * bb + c * 8, pw);
                     }
                 }
                 l_sum += (rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y) + (rs2[2].x + rs2[2].y) + (rs2[3].x + rs2[3].y);
+                if (quarter == 0) ATT_TR(i, t, 4);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(p_full(i));
+                if (quarter == 0) ATT_TR(i, t, 5);
+                mbar_arrive(p_full(i, bb));
+                if (quarter == 0) ATT_TR(i, t, 6);
             }
-            // ---- epilogue: O / l -> bf16, token-major; the two halves first add up their row sums
-            xst(xslot(n_kv & 1, half), l_sum);
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            l_sum += xld(xslot(n_kv & 1, half ^ 1));
+            // ---- epilogue: O / l -> bf16, token-major
             mbar_wait(o_full(i), 0, 31);
             tc_fence_after();
             const float inv = 1.0f / l_sum;
-            __nv_bfloat16* orow = p.out + ((int64_t)b * p.L + qrow) * p.ldo + h * HD + half * (HD / 2);
+            __nv_bfloat16* orow = p.out + ((int64_t)b * p.L + qrow) * p.ldo + h * HD;
 #pragma unroll 1
-            for (int c = 0; c < HD / 64; ++c) {
+            for (int c = 0; c < HD / 32; ++c) {
                 uint32_t ov[32];
                 tmem_ld_32x32b_x32(t_o + c * 32, ov);
                 tmem_ld_wait();
                 if (qrow < p.L) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
+                    for (int u = 0; u < 4; ++u) {
                         uint4 w;
-                        w.x = pack_bf16(__uint_as_float(ov[8 * t + 0]) * inv, __uint_as_float(ov[8 * t + 1]) * inv);
-                        w.y = pack_bf16(__uint_as_float(ov[8 * t + 2]) * inv, __uint_as_float(ov[8 * t + 3]) * inv);
-                        w.z = pack_bf16(__uint_as_float(ov[8 * t + 4]) * inv, __uint_as_float(ov[8 * t + 5]) * inv);
-                        w.w = pack_bf16(__uint_as_float(ov[8 * t + 6]) * inv, __uint_as_float(ov[8 * t + 7]) * inv);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + 8 * t) = w;
+                        w.x = pack_bf16(__uint_as_float(ov[8 * u + 0]) * inv, __uint_as_float(ov[8 * u + 1]) * inv);
+                        w.y = pack_bf16(__uint_as_float(ov[8 * u + 2]) * inv, __uint_as_float(ov[8 * u + 3]) * inv);
+                        w.z = pack_bf16(__uint_as_float(ov[8 * u + 4]) * inv, __uint_as_float(ov[8 * u + 5]) * inv);
+                        w.w = pack_bf16(__uint_as_float(ov[8 * u + 6]) * inv, __uint_as_float(ov[8 * u + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + 8 * u) = w;
                     }
                 }
             }
@@ -373,7 +364,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
 }
 
-template <int HD>
+#ifdef MMADA_ATT_TRACE
+static long long* g_attn_trace = nullptr;
+#endif
+
+template <int HD, int POLY>
 static int launch_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                             int H, float scale, cudaStream_t stream) {
     using Cfg = AttnCfg<HD>;
@@ -385,7 +380,7 @@ static int launch_attention(const void* q, const void* k, const void* v, int64_t
     if ((st = make_tmap(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, strides, box))) return st;
     if ((st = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box))) return st;
     if ((st = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box))) return st;
-    auto kern = attention_kernel<HD>;
+    auto kern = attention_kernel<HD, POLY>;
     static bool configured = false;
     if (!configured) {
         MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -396,14 +391,47 @@ static int launch_attention(const void* q, const void* k, const void* v, int64_t
     p.ldo = ldo;
     p.L = L; p.H = H; p.B = B;
     p.scale_log2 = scale * 1.4426950408889634f;
+#ifdef MMADA_ATT_TRACE
+    p.trace = g_attn_trace;
+#endif
     const int q_pairs = (L + 2 * QT - 1) / (2 * QT);
     kern<<<B * H * q_pairs, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, p);
     return cuda_status(cudaGetLastError());
 }
 
+// share of the exponentials on the FMA pipe, in eighths (tuning knob; default set from measurements)
+static int attention_poly_eighths() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MMADA_ATT_POLY");
+        v = e ? atoi(e) : kAttnPolyDefault;
+        if (v != 0 && v != 2 && v != 3 && v != 4) v = kAttnPolyDefault;
+    }
+    return v;
+}
+
+template <int HD>
+static int dispatch_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                              int H, float scale, cudaStream_t stream) {
+    switch (attention_poly_eighths()) {
+        case 0: return launch_attention<HD, 0>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+        case 2: return launch_attention<HD, 2>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+        case 3: return launch_attention<HD, 3>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+        default: return launch_attention<HD, 4>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+    }
+}
+
+// attention_pair.cu: persistent CTA pairs, head_dim 128
+int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                          int H, float scale, int poly, cudaStream_t stream);
+
 }  // namespace mmada
 
 using namespace mmada;
+
+#ifdef MMADA_ATT_TRACE
+extern "C" void mmada_attention_set_trace(void* buf) { mmada::g_attn_trace = (long long*)buf; }
+#endif
 
 extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo,
                                     int B, int L, int H, int head_dim, float scale, void* stream) {
@@ -413,7 +441,15 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
          reinterpret_cast<uintptr_t>(out)) & 15)
         return kBadArgument;
     cudaStream_t s = (cudaStream_t)stream;
-    if (head_dim == 128) return launch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, s);
-    if (head_dim == 64) return launch_attention<64>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+    if (head_dim == 128) {
+        static int use_pair = -1;       // MMADA_ATT_PAIR=0 selects the single-CTA kernel (kept for head_dim 64 and A/B runs)
+        if (use_pair < 0) {
+            const char* e = getenv("MMADA_ATT_PAIR");
+            use_pair = e ? atoi(e) != 0 : 1;
+        }
+        if (use_pair && L > 128) return launch_attention_pair(q, k, v, ld, out, ldo, B, L, H, scale, attention_poly_eighths(), s);
+        return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+    }
+    if (head_dim == 64) return dispatch_attention<64>(q, k, v, ld, out, ldo, B, L, H, scale, s);
     return kUnsupportedShape;
 }

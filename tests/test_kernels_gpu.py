@@ -129,7 +129,9 @@ def test_embed():
 
 
 @pytest.mark.parametrize("hd", [64, 128], ids=["hd64", "hd128"])
-@pytest.mark.parametrize("B,H,L", [(1, 2, 128), (2, 3, 387), (2, 2, 1539), (1, 1, 100), (1, 2, 256), (1, 1, 257)])
+@pytest.mark.parametrize("B,H,L", [(1, 2, 128), (2, 3, 387), (2, 2, 1539), (1, 1, 100), (1, 2, 256), (1, 1, 257),
+                                   # more work items than CTA pairs: the persistent path (buffer reuse, phase flips)
+                                   (2, 40, 700), (3, 60, 130), (5, 32, 1024)])
 def test_attention(hd, B, H, L):
     from mmada_b200 import ops
     d = H * hd
