@@ -146,6 +146,13 @@ int mmada_cast_f32_bf16(const float* x, void* out_bf16, int64_t n, void* stream)
 int mmada_softmax_rows_bf16(const float* x, void* out_bf16, int R, int n, float scale, void* stream);
 int mmada_nhwc_to_nchw_f32(const float* x, float* out, int B, int P, int C, void* stream);
 int mmada_image_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
+/* Encoder side (MAGVITv2.get_code, models/modeling_magvitv2.py:143-169,423-427).  image_to_nhwc64: pixel_values
+ * fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64], channels 3..63 zero (conv_in input).  space_to_depth2: fp32 NHWC
+ * [B,H,W,C] -> bf16 NHWC [B,H/2,W/2,4C], channel (2sy+sx)C+c = pixel (2y+sy, 2x+sx): Downsample
+ * (models/common_modules.py:73-90, pad (0,1,0,1) + 3x3 stride 2) then runs as a stride-1 3x3 convolution whose
+ * weights the host has rearranged (taps reaching above / left of the block are zero).                          */
+int mmada_image_to_nhwc64_bf16(const float* pixels_nchw, void* out_bf16, int B, int H, int W, void* stream);
+int mmada_space_to_depth2_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mmada_softmax_rows_bf16": [_p, _p, _i, _i, _f, _p],
     "mmada_nhwc_to_nchw_f32": [_p, _p, _i, _i, _i, _p],
     "mmada_image_to_uint8": [_p, _p, _i64, _p],
+    "mmada_image_to_nhwc64_bf16": [_p, _p, _i, _i, _i, _p],
+    "mmada_space_to_depth2_bf16": [_p, _p, _i, _i, _i, _i, _p],
 }
 
 

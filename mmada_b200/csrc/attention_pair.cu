@@ -513,10 +513,10 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
 // head_dim 128 entry used by mmada_attention_bf16 (attention.cu); poly = eighths of the exponentials on the FMA pipe
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int H, float scale, int poly, cudaStream_t stream) {
-    static int token = -1;              // MMADA_ATT_TOKEN=0: let the two warps of a scheduler drift freely (A/B runs)
+    static int token = -1;              // MMADA_ATT_TOKEN=1: pass a token between the two warps of a scheduler around the exponentials (A/B runs; measured slower)
     if (token < 0) {
         const char* e = getenv("MMADA_ATT_TOKEN");
-        token = e ? atoi(e) != 0 : 1;
+        token = e ? atoi(e) != 0 : 0;
     }
     if (token) {
         switch (poly) {

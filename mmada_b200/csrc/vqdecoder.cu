@@ -203,6 +203,43 @@ static inline int grid_for(int64_t work, int threads = 256) {
 
 using namespace mmada;
 
+// ---- encoder side (MAGVITv2.get_code: models/modeling_magvitv2.py:143-169, 423-427) ----------------------------
+// pixel_values fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64] (channels 3..63 zero): the input of conv_in as an
+// implicit GEMM with one whole 64-channel k-block per tap.
+__global__ void image_to_nhwc64_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int P, int64_t total) {
+    // one thread per (pixel, 8-channel group): 8 groups of 16 bytes per pixel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(i & 7);
+        const int64_t pix = i >> 3;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (grp == 0) {
+            const int64_t b = pix / P, pp = pix - b * P;
+            const float* src = x + b * 3 * (int64_t)P + pp;
+            w.x = pack_bf16(src[0], src[P]);
+            w.y = pack_bf16(src[2 * (int64_t)P], 0.f);
+        }
+        reinterpret_cast<uint4*>(out)[i] = w;
+    }
+}
+// Downsample (models/common_modules.py:73-90: zero-pad right/bottom by one, 3x3 convolution with stride 2) runs as
+// a stride-1 convolution over the SPACE-TO-DEPTH image: fp32 NHWC [B,H,W,C] -> bf16 NHWC [B,H/2,W/2,4C], channel
+// (2 sy + sx) C + c = pixel (2y + sy, 2x + sx).  The host rearranges the 3x3 weights accordingly.
+__global__ void space_to_depth2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int H, int W, int C,
+                                       int64_t total4) {
+    const int C4 = C >> 2, Ho = H >> 1, Wo = W >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        // i indexes the OUTPUT in units of 4 channels
+        const int c4 = (int)(i % C4);
+        int64_t r = i / C4;
+        const int s = (int)(r & 3); r >>= 2;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho);
+        const int64_t b = r / Ho;
+        const float4 v = *reinterpret_cast<const float4*>(x + (((b * H + 2 * yo + (s >> 1)) * W + 2 * xo + (s & 1)) * (int64_t)C + 4 * c4));
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+}
+
 extern "C" int mmada_lfq_decode_nhwc(const int64_t* indices, const float* pq_weight, const float* pq_bias, void* out_bf16,
                                      int total_tokens, void* stream) {
     if (!indices || !pq_weight || !pq_bias || !out_bf16 || total_tokens <= 0) return kBadArgument;
@@ -265,5 +302,18 @@ extern "C" int mmada_nhwc_to_nchw_f32(const float* x, float* out, int B, int P, 
 extern "C" int mmada_image_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream) {
     if (!x || !out || n <= 0) return kBadArgument;
     image_to_uint8_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+    return cuda_status(cudaGetLastError());
+}
+extern "C" int mmada_image_to_nhwc64_bf16(const float* pixels_nchw, void* out_bf16, int B, int H, int W, void* stream) {
+    if (!pixels_nchw || !out_bf16 || B <= 0 || H <= 0 || W <= 0) return kBadArgument;
+    const int64_t total = (int64_t)B * H * W * 8;
+    image_to_nhwc64_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(pixels_nchw, (__nv_bfloat16*)out_bf16, H * W, total);
+    return cuda_status(cudaGetLastError());
+}
+extern "C" int mmada_space_to_depth2_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream) {
+    if (!x || !out_bf16 || B <= 0 || H <= 0 || W <= 0 || C <= 0) return kBadArgument;
+    if ((H & 1) || (W & 1) || (C & 3)) return kUnsupportedShape;
+    const int64_t total4 = (int64_t)B * H * W * C / 4;
+    space_to_depth2_kernel<<<grid_for(total4), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, H, W, C, total4);
     return cuda_status(cudaGetLastError());
 }

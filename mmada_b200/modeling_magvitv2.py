@@ -7,7 +7,9 @@ convolution input is the bf16 output of the fused GroupNorm(+swish) kernel (or a
 upsample of the trunk), so convolutions run as bf16 implicit GEMMs on tcgen05 with fp32 accumulation
 and fp32 bias / residual epilogues.  The reference runs this model in fp32 (Q18); the stated
 tolerance of the parity tests reflects the bf16 operands.
-``get_code`` (the VQGAN encoder) is the next row of SURVEY.md 8(f) and is not built yet.
+``get_code`` (pixel -> token side, SURVEY.md 8(f) item 1: ``VQGANEncoder.forward`` :143-169 + the LFQ sign test
+:201-206,236-241) reuses the same kernels; its stride-2 ``Downsample`` convolutions run as stride-1 convolutions
+over a space-to-depth image with rearranged weights.
 """
 from __future__ import annotations
 
@@ -19,6 +21,24 @@ import torch
 from . import ops
 
 CH, CH_MULT, NUM_RES, Z_CH = 128, (1, 1, 2, 2, 4), (4, 4, 3, 4, 3), 13
+ENC_CH_MULT, ENC_NUM_RES = (1, 2, 2, 4, 4), (4, 3, 4, 3, 4)          # VQGANEncoder defaults (modeling_magvitv2.py:49-72)
+
+
+def encoder_plan():
+    """(kind, key, c_in, c_out) in execution order (modeling_magvitv2.py:74-141 / :143-169); no attention in the
+    down path (attn_resolutions [5] never matches)."""
+    plan = [("conv_in", "conv_in", 3, CH)]
+    c = CH
+    for lvl in range(5):
+        co = CH * ENC_CH_MULT[lvl]
+        for j in range(ENC_NUM_RES[lvl]):
+            plan.append(("res", f"down.{lvl}.block.{j}", c, co))
+            c = co
+        if lvl != 4:
+            plan.append(("down", f"down.{lvl}.downsample", c, c))
+    plan += [("res", "mid.block_1", c, c), ("attn", "mid.attn_1", c, c), ("res", "mid.block_2", c, c),
+             ("out", "conv_out", c, Z_CH)]
+    return plan
 
 
 def decoder_plan():
@@ -61,22 +81,68 @@ class MAGVITv2:
         self.kernel_launches = 0
 
     # ---- weights ---------------------------------------------------------------------------
-    def _conv(self, sd, key, pad_cin_to: Optional[int] = None):
-        wt = sd[f"decoder.{key}.weight"].to(self.device, torch.float32)          # [Cout, Cin, kh, kw]
+    def _conv(self, sd, key, pad_cin_to: Optional[int] = None, src="decoder.", dst=""):
+        wt = sd[f"{src}{key}.weight"].to(self.device, torch.float32)             # [Cout, Cin, kh, kw]
         co, ci, kh, kw = wt.shape
         wt = wt.permute(0, 2, 3, 1)                                              # [Cout, kh, kw, Cin]
         if pad_cin_to is not None and pad_cin_to > ci:
             wt = torch.nn.functional.pad(wt, (0, pad_cin_to - ci))
-        self.w[key + ".w"] = wt.reshape(co, -1).to(torch.bfloat16).contiguous()
-        self.w[key + ".b"] = sd[f"decoder.{key}.bias"].to(self.device, torch.float32).contiguous()
+        self.w[dst + key + ".w"] = wt.reshape(co, -1).to(torch.bfloat16).contiguous()
+        self.w[dst + key + ".b"] = sd[f"{src}{key}.bias"].to(self.device, torch.float32).contiguous()
 
-    def _norm(self, sd, key):
-        self.w[key + ".g"] = sd[f"decoder.{key}.weight"].to(self.device, torch.float32).contiguous()
-        self.w[key + ".beta"] = sd[f"decoder.{key}.bias"].to(self.device, torch.float32).contiguous()
+    def _norm(self, sd, key, src="decoder.", dst=""):
+        self.w[dst + key + ".g"] = sd[f"{src}{key}.weight"].to(self.device, torch.float32).contiguous()
+        self.w[dst + key + ".beta"] = sd[f"{src}{key}.bias"].to(self.device, torch.float32).contiguous()
+
+    def _load_encoder(self, sd):
+        """``encoder.*`` keys -> self.w["enc." + ...].  Downsample: w[co,ci,ky,kx] (stride 2 on the image padded right /
+        bottom) becomes a stride-1 3x3 kernel over the space-to-depth image: pixel (2y+ky, 2x+kx) is sub-pixel
+        (ky%2, kx%2) of block (y + ky//2, x + kx//2), i.e. tap (ky//2, kx//2) in {0,1}^2 of the 3x3 window centred on
+        the block; taps reaching above / left stay zero.  quant_conv (1x1, linear) is folded into conv_out."""
+        E = "enc."
+        for kind, key, ci, co in encoder_plan():
+            if kind == "conv_in":
+                self._conv(sd, key, pad_cin_to=64, src="encoder.", dst=E)
+            elif kind == "res":
+                self._norm(sd, key + ".norm1", "encoder.", E); self._conv(sd, key + ".conv1", src="encoder.", dst=E)
+                self._norm(sd, key + ".norm2", "encoder.", E); self._conv(sd, key + ".conv2", src="encoder.", dst=E)
+                if ci != co:
+                    self._conv(sd, key + ".nin_shortcut", src="encoder.", dst=E)
+            elif kind == "attn":
+                self._norm(sd, key + ".norm", "encoder.", E)
+                for n in ("q", "k", "v", "proj_out"):
+                    self._conv(sd, f"{key}.{n}", src="encoder.", dst=E)
+                self.w[E + key + ".qk.w"] = torch.cat([self.w[E + key + ".q.w"], self.w[E + key + ".k.w"]], 0).contiguous()
+                self.w[E + key + ".qk.b"] = torch.cat([self.w[E + key + ".q.b"], self.w[E + key + ".k.b"]], 0).contiguous()
+            elif kind == "down":
+                wt = sd[f"encoder.{key}.conv.weight"].to(self.device, torch.float32)          # [C, C, 3, 3]
+                C = wt.shape[0]
+                w2 = torch.zeros((C, 3, 3, 4, C), device=self.device, dtype=torch.float32)    # [co, ty, tx, sub, ci]
+                for ky in range(3):
+                    for kx in range(3):
+                        w2[:, ky // 2 + 1, kx // 2 + 1, 2 * (ky % 2) + (kx % 2), :] = wt[:, :, ky, kx]
+                self.w[E + key + ".w"] = w2.reshape(C, -1).to(torch.bfloat16).contiguous()
+                self.w[E + key + ".b"] = sd[f"encoder.{key}.conv.bias"].to(self.device, torch.float32).contiguous()
+            elif kind == "out":
+                self._norm(sd, "norm_out", "encoder.", E)
+                wc = sd["encoder.conv_out.weight"].to(self.device, torch.float32)             # [13, C, 3, 3]
+                bc = sd["encoder.conv_out.bias"].to(self.device, torch.float32)
+                wq = sd["encoder.quant_conv.weight"].to(self.device, torch.float32).reshape(Z_CH, Z_CH)
+                bq = sd["encoder.quant_conv.bias"].to(self.device, torch.float32)
+                wf = torch.einsum("oz,zchw->ochw", wq, wc).permute(0, 2, 3, 1)                # quant_conv o conv_out
+                self.w[E + "conv_out.w"] = wf.reshape(Z_CH, -1).to(torch.bfloat16).contiguous()
+                self.w[E + "conv_out.b"] = (wq @ bc + bq).contiguous()
+        self.has_encoder = True
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False) -> "MAGVITv2":
-        """``sd`` uses the reference's key names (``decoder.*``); encoder keys are ignored."""
+        """``sd`` uses the reference's key names (``decoder.*`` and, for ``get_code``, ``encoder.*``; SURVEY.md
+        Appendix D).  Either half may be absent."""
         self.w = {}
+        self.has_encoder = False
+        if any(k.startswith("encoder.") for k in sd):
+            self._load_encoder(sd)
+        if not any(k.startswith("decoder.") for k in sd):
+            return self
         self.w["pq.w"] = sd["decoder.post_quant_conv.weight"].to(self.device, torch.float32).reshape(13, 13).contiguous()
         self.w["pq.b"] = sd["decoder.post_quant_conv.bias"].to(self.device, torch.float32).contiguous()
         for kind, key, ci, co in decoder_plan():
@@ -148,6 +214,33 @@ class MAGVITv2:
             x = self._c(ops.cast_bf16(x), key + ".nin_shortcut", 1)
         return self._c(h, key + ".conv2", 9, resid=x)
 
+    @torch.no_grad()
+    def _encode_nhwc(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """fp32 NCHW pixels -> pre-quantisation latents fp32 NHWC [B, H/16, W/16, 13] (quant_conv included)."""
+        if not getattr(self, "has_encoder", False):
+            raise ops._lib.MMadaKernelError("MAGVITv2.get_code: no encoder weights loaded (state dict had no 'encoder.*' keys)")
+        px = pixel_values.to(self.device, torch.float32).contiguous()
+        B, _, H, W = px.shape
+        if H % 16 or W % 16:
+            raise ValueError("get_code: image sides must be multiples of 16")
+        self._sums = torch.empty((B, 32, 2), device=self.device, dtype=torch.float64)
+        x = ops.image_to_nhwc64(px)
+        self.kernel_launches += 1
+        E = "enc."
+        for kind, key, ci, co in encoder_plan():
+            if kind == "conv_in":
+                x = self._c(x, E + key, 9)
+            elif kind == "res":
+                x = self._res(x, E + key, ci, co)
+            elif kind == "attn":
+                x = self._attn(x, E + key)
+            elif kind == "down":
+                self.kernel_launches += 1
+                x = self._c(ops.space_to_depth2(x), E + key, 9)
+            elif kind == "out":
+                x = self._c(self._gn(x, E + "norm_out"), E + key, 9)
+        return x
+
     def _attn(self, x, key):
         B, H, W, C = x.shape
         P = H * W
@@ -199,5 +292,17 @@ class MAGVITv2:
         self.kernel_launches += 1
         return ops.image_to_uint8(self._decode_nhwc(codebook_indices, shape))
 
-    def get_code(self, pixel_values):
-        raise NotImplementedError("MAGVITv2.get_code (VQGAN encoder) is not built yet: SURVEY.md 8(f) item 1")
+    @torch.no_grad()
+    def encode_latents(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """``self.encoder(pixel_values)`` of the reference: fp32 (B, 13, H/16, W/16), before the sign test."""
+        self.kernel_launches += 1
+        return ops.nhwc_to_nchw(self._encode_nhwc(pixel_values))
+
+    @torch.no_grad()
+    def get_code(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """(B, 3, H, W) fp32 pixels -> (B, H/16 * W/16) int64 code ids (modeling_magvitv2.py:423-427):
+        bit k of the code = [latent channel k > 0], MSB first."""
+        z = self.encode_latents(pixel_values)
+        B = z.shape[0]
+        self.kernel_launches += 1
+        return self.quantize.get_indices(z).reshape(B, -1)

@@ -313,3 +313,23 @@ def image_to_uint8(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
     _lib.call("mmada_image_to_uint8", x.contiguous().data_ptr(), out.data_ptr(), x.numel(), _stream())
     return out
+
+
+def image_to_nhwc64(pixel_values: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW [B,3,H,W] -> bf16 NHWC [B,H,W,64] (channels 3.. zero)."""
+    _chk(pixel_values, torch.float32, "pixel_values")
+    B, C, H, W = pixel_values.shape
+    assert C == 3
+    out = torch.empty((B, H, W, 64), device=pixel_values.device, dtype=torch.bfloat16)
+    _lib.call("mmada_image_to_nhwc64_bf16", pixel_values.contiguous().data_ptr(), out.data_ptr(), B, H, W, _stream())
+    return out
+
+
+def space_to_depth2(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NHWC [B,H,W,C] -> bf16 NHWC [B,H/2,W/2,4C], channel (2*sy+sx)*C + c = pixel (2y+sy, 2x+sx)."""
+    _chk(x, torch.float32, "x")
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B, H // 2, W // 2, 4 * C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_space_to_depth2_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    return out

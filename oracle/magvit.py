@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows
   * /root/reference/models/modeling_magvitv2.py:186-221   LFQuantizer tables / get_indices / get_codebook_entry
   * /root/reference/models/modeling_magvitv2.py:365-399   VQGANDecoder.forward
   * /root/reference/models/modeling_magvitv2.py:429-433   MAGVITv2.decode_code
+  * /root/reference/models/modeling_magvitv2.py:143-169   VQGANEncoder.forward; :423-427 MAGVITv2.get_code;
+    :236-241 the quantiser's sign test; common_modules.py:73-90 Downsample (pad (0,1,0,1) + 3x3 stride 2)
   * /root/reference/models/common_modules.py:16-40,168-211,298-357  swish, GroupNorm(32, eps 1e-6),
     Upsample (nearest 2x + conv3x3), AttnBlock, ResnetBlock
 The bit <-> index maps are restated in numpy (integer work); the decoder in fp32 torch.
@@ -17,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .weights import vq_decoder_plan
+from .weights import vq_decoder_plan, vq_encoder_plan
 
 CODE_BITS = 13
 
@@ -98,3 +100,33 @@ def decoder_forward(z: torch.Tensor, sd: Dict[str, torch.Tensor], taps: Optional
 def decode_code(indices: torch.Tensor, sd: Dict[str, torch.Tensor], taps: Optional[dict] = None) -> torch.Tensor:
     z = torch.from_numpy(lfq_indices_to_bits(indices.cpu().numpy()))
     return decoder_forward(z, sd, taps)
+
+
+def encoder_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], taps: Optional[dict] = None) -> torch.Tensor:
+    """pixels (B, 3, H, W) fp32 -> pre-quantisation latents (B, 13, H/16, W/16) fp32 (quant_conv included).
+    ``sd`` keys are prefixed 'encoder.'."""
+    h = x
+    for kind, key, ci, co in vq_encoder_plan():
+        k = "encoder." + key
+        if kind == "conv1":
+            h = _conv(h, sd, k, 0)
+        elif kind == "conv3":
+            h = _conv(h, sd, k, 1)
+        elif kind == "res":
+            h = _res(h, sd, k, ci, co)
+        elif kind == "attn":
+            h = _attn(h, sd, k)
+        elif kind == "down":
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd[k + ".conv.weight"], sd[k + ".conv.bias"],
+                         stride=2, padding=0)
+        elif kind == "norm_out":
+            h = _swish(_gn(h, sd, k))
+        if taps is not None:
+            taps[key] = h
+    return h
+
+
+def get_code(pixels: torch.Tensor, sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """(B, 3, H, W) -> (B, H/16 * W/16) int64: bit k of the code = [latent channel k > 0] (z_q = +-1 by sign)."""
+    z = encoder_forward(pixels, sd)
+    return torch.from_numpy(lfq_bits_to_indices(z.numpy())).reshape(pixels.shape[0], -1)

@@ -214,6 +214,27 @@ def magvit_case():
           bits_sample=vq.quantize.get_codebook_entry(torch.tensor([[0, 5, 4096, 8191]])), **out)
 
 
+def magvit_encoder_case():
+    """MAGVITv2.get_code: the real reference's encoder on synthetic weights, 256 x 256 input
+    (16 x 16 tokens: the smallest grid the GPU convolution tiling accepts)."""
+    print("[magvit encoder]")
+    sd = W.make_vq_encoder_weights(0)
+    vq = rb.build_vq(sd)
+    g = torch.Generator().manual_seed(11)
+    # smooth-ish image in [-1, 1]: low-resolution noise upsampled, plus fine noise
+    base = torch.nn.functional.interpolate(torch.randn(1, 3, 16, 16, generator=g), size=(256, 256), mode="bilinear")
+    px = (0.6 * base + 0.2 * torch.randn(1, 3, 256, 256, generator=g)).clamp(-1, 1)
+    px = px.to(torch.float16).float()          # the fixture stores fp16: both sides get exactly these values
+    with torch.no_grad():
+        ref_z = vq.encoder(px)
+        ref_codes = vq.get_code(px)
+    mine_z = magvit.encoder_forward(px, sd)
+    assert torch.equal(ref_z, mine_z), "restatement != reference (encoder)"
+    assert torch.equal(ref_codes, magvit.get_code(px, sd)), "restatement != reference (get_code)"
+    _save("magvit_encoder", pixels=px.to(torch.float16), latents=ref_z, codes=ref_codes,
+          latent_absmax=ref_z.abs().max(), note=np.array("pixels are exactly representable in fp16: feed pixels.float()"))
+
+
 def logits_case(name, cfg, B, L, wseed, seed):
     print(f"[logits] {name}")
     sd = W.make_llada_weights(cfg, wseed)
@@ -237,6 +258,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     sampling_case()
     magvit_case()
+    magvit_encoder_case()
     logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
     logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
     t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)

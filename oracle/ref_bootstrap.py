@@ -85,7 +85,8 @@ def build_vq(state_dict=None):
     if state_dict is not None:
         missing, unexpected = vq.load_state_dict(state_dict, strict=False)
         assert not unexpected, unexpected
-        assert all(not m.startswith("decoder.") for m in missing), missing
+        have = {k.split(".")[0] for k in state_dict}
+        assert all(m.split(".")[0] not in have or m.startswith("quantize.") for m in missing), missing
     return vq
 
 

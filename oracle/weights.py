@@ -158,3 +158,60 @@ def make_vq_decoder_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
         elif kind == "norm_out":
             norm(key, ci)
     return sd
+
+
+# --- MAGVIT-v2 encoder --------------------------------------------------------------------
+
+VQ_ENC_CH_MULT, VQ_ENC_NUM_RES = (1, 2, 2, 4, 4), (4, 3, 4, 3, 4)
+
+
+def vq_encoder_plan():
+    """Encoder topology as a flat list of (kind, key-prefix, c_in, c_out), following reference
+    models/modeling_magvitv2.py:74-141 (construction) / :143-169 (forward).  attn_resolutions [5] never
+    matches a feature-map size, so the down path has no attention blocks."""
+    plan = [("conv3", "conv_in", 3, VQ_CH)]
+    c = VQ_CH
+    for lvl in range(5):
+        co = VQ_CH * VQ_ENC_CH_MULT[lvl]
+        for j in range(VQ_ENC_NUM_RES[lvl]):
+            plan.append(("res", f"down.{lvl}.block.{j}", c, co))
+            c = co
+        if lvl != 4:
+            plan.append(("down", f"down.{lvl}.downsample", c, c))
+    plan += [("res", "mid.block_1", c, c), ("attn", "mid.attn_1", c, c), ("res", "mid.block_2", c, c),
+             ("norm_out", "norm_out", c, c), ("conv3", "conv_out", c, VQ_Z), ("conv1", "quant_conv", VQ_Z, VQ_Z)]
+    return plan
+
+
+def make_vq_encoder_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for ``MAGVITv2.encoder`` with the reference's key names, prefixed 'encoder.'."""
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, co, ci, k):
+        std = 1.0 / math.sqrt(ci * k * k)
+        sd[f"encoder.{name}.weight"] = _normal(seed, "enc." + name + ".w", (co, ci, k, k), std)
+        sd[f"encoder.{name}.bias"] = _normal(seed, "enc." + name + ".b", (co,), 0.02)
+
+    def norm(name, c):
+        sd[f"encoder.{name}.weight"] = 1.0 + _normal(seed, "enc." + name + ".w", (c,), 0.1)
+        sd[f"encoder.{name}.bias"] = _normal(seed, "enc." + name + ".b", (c,), 0.05)
+
+    for kind, key, ci, co in vq_encoder_plan():
+        if kind == "conv1":
+            conv(key, co, ci, 1)
+        elif kind == "conv3":
+            conv(key, co, ci, 3)
+        elif kind == "res":
+            norm(key + ".norm1", ci); conv(key + ".conv1", co, ci, 3)
+            norm(key + ".norm2", co); conv(key + ".conv2", co, co, 3)
+            if ci != co:
+                conv(key + ".nin_shortcut", co, ci, 1)
+        elif kind == "attn":
+            norm(key + ".norm", ci)
+            for n in ("q", "k", "v", "proj_out"):
+                conv(f"{key}.{n}", co, ci, 1)
+        elif kind == "down":
+            conv(key + ".conv", co, ci, 3)
+        elif kind == "norm_out":
+            norm(key, ci)
+    return sd

@@ -100,5 +100,61 @@ def test_decode_code_vs_reference_golden(golden):
     u8 = vq.decode_code_uint8(idx)
     exp = (torch.clamp((pix + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).cpu().numpy().astype(np.uint8)
     assert np.array_equal(u8.cpu().numpy(), exp)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(Exception, match="no encoder weights"):
         vq.get_code(pix)
+
+
+def test_encoder_input_and_downsample_kernels():
+    """image_to_nhwc64 and the space-to-depth formulation of Downsample (pad (0,1,0,1) + 3x3 stride 2,
+    models/common_modules.py:73-90) against PyTorch on the same bf16-rounded operands."""
+    from mmada_b200 import ops
+    from mmada_b200.modeling_magvitv2 import MAGVITv2
+    g = torch.Generator(device="cuda").manual_seed(7)
+    px = torch.randn(2, 3, 32, 48, device="cuda", generator=g)
+    x64 = ops.image_to_nhwc64(px)
+    assert x64.shape == (2, 32, 48, 64)
+    assert torch.equal(x64[..., :3], px.permute(0, 2, 3, 1).bfloat16()) and int(x64[..., 3:].abs().sum()) == 0
+    B, H, W, C = 2, 64, 64, 128
+    x = torch.randn(B, H, W, C, device="cuda", generator=g)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)
+    b = torch.randn(C, device="cuda", generator=g)
+    vq = MAGVITv2()
+    sd = {"encoder.down.0.downsample.conv.weight": w, "encoder.down.0.downsample.conv.bias": b}
+    # reuse the loader's weight rearrangement for one Downsample layer
+    w2 = torch.zeros((C, 3, 3, 4, C), device="cuda")
+    for ky in range(3):
+        for kx in range(3):
+            w2[:, ky // 2 + 1, kx // 2 + 1, 2 * (ky % 2) + (kx % 2), :] = w[:, :, ky, kx]
+    s2d = ops.space_to_depth2(x)
+    assert s2d.shape == (B, H // 2, W // 2, 4 * C)
+    assert torch.equal(s2d[:, 3, 5, 2 * C:3 * C], x[:, 7, 10].bfloat16())          # sub-pixel (1, 0) of block (3, 5)
+    out = ops.conv_nhwc(s2d, w2.reshape(C, -1).bfloat16().contiguous(), b, 9, ops.EPI_BIAS_F32)
+    xr = F.pad(x.bfloat16().float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xr, w.bfloat16().float(), b, stride=2).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and _rel(out, ref) < 2e-5
+
+
+def test_get_code_vs_reference_golden(golden):
+    """MAGVITv2.get_code on the synthetic encoder weights against the real reference (fp32): latents within the
+    stated tolerance; the code ids bit-exact given OUR latents (the LFQ sign test is integer work), and their
+    agreement with the reference's ids reported (a bf16-operand latent within 1e-2 of zero may flip its bit)."""
+    from mmada_b200.modeling_magvitv2 import MAGVITv2
+    from oracle import magvit, weights as W
+    gd = golden("magvit_encoder")
+    vq = MAGVITv2().load_state_dict(W.make_vq_encoder_weights(0))
+    px = torch.from_numpy(gd["pixels"]).float().cuda()
+    z = vq.encode_latents(px)
+    ref = torch.from_numpy(gd["latents"])
+    assert z.shape == ref.shape == (1, 13, 16, 16)
+    err = float((z.cpu() - ref).abs().max()) / float(gd["latent_absmax"])
+    rms = float((z.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    codes = vq.get_code(px)
+    assert codes.shape == (1, 256) and codes.dtype == torch.int64
+    assert np.array_equal(codes.cpu().numpy(), magvit.lfq_bits_to_indices(z.cpu().numpy()).reshape(1, -1))
+    ref_codes = torch.from_numpy(gd["codes"])
+    bits_equal = 1.0 - float(((codes.cpu() ^ ref_codes).unsqueeze(-1) >> torch.arange(13) & 1).float().mean())
+    print(f"get_code 256x256: latents max|d|/max|ref| = {err:.3e}, rel-rms = {rms:.3e}; "
+          f"bit agreement with the fp32 reference {bits_equal:.4f}, id agreement {float((codes.cpu() == ref_codes).float().mean()):.3f}")
+    # bf16 conv operands (fp32 accumulate, fp32 trunk) through ~50 conv layers vs the fp32 reference
+    assert err < 3e-2 and rms < 2e-2
+    assert bits_equal > 0.97

@@ -105,3 +105,14 @@ def test_t2m_tiny(golden):
     assert np.array_equal(out.numpy(), gd["sampled_ids"])
     assert np.array_equal(ids.numpy(), gd["final_input_ids"])
     assert int((ids == 126336).sum()) == 0            # Q15: no re-masking on the last step
+
+
+def test_magvit_encoder(golden):
+    """get_code: the restated VQGAN encoder reproduces the real reference's latents and code ids bit for bit."""
+    gd = golden("magvit_encoder")
+    sd = W.make_vq_encoder_weights(0)
+    px = torch.from_numpy(gd["pixels"]).float()
+    with torch.no_grad():
+        z = magvit.encoder_forward(px, sd)
+    assert np.array_equal(z.numpy(), gd["latents"])
+    assert np.array_equal(magvit.lfq_bits_to_indices(z.numpy()).reshape(1, -1), gd["codes"])
