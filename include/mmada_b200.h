@@ -153,6 +153,14 @@ int mmada_image_to_uint8(const float* x, uint8_t* out, int64_t n, void* stream);
  * weights the host has rearranged (taps reaching above / left of the block are zero).                          */
 int mmada_image_to_nhwc64_bf16(const float* pixels_nchw, void* out_bf16, int B, int H, int W, void* stream);
 int mmada_space_to_depth2_bf16(const float* x, void* out_bf16, int B, int H, int W, int C, void* stream);
+/* Motion VQ-VAE decoder (motion_vqvae/models/encdec.py:35-67, resnet.py:12-81; VQVAE_251.forward_decoder
+ * vqvae.py:74-81).  conv1d_gather: x fp32 [B,T_in,C] -> bf16 [B, T_in*upsample, taps*C]: for output frame t the
+ * frames t + (k - taps/2)*dilation of the (nearest-2x upsampled, if upsample == 2) sequence side by side, zero
+ * outside [0, T_out), optional ReLU on the way; the Conv1d is then mmada_gemm_bf16 with weight [C_out, taps*C].
+ * relu_f32: in place.                                                                                       */
+int mmada_conv1d_gather_bf16(const float* x, void* out_bf16, int B, int T_in, int C, int taps, int dilation,
+                             int upsample, int relu, void* stream);
+int mmada_relu_f32(float* x, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

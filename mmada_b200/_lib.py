@@ -45,6 +45,8 @@ SIGNATURES = {
     "mmada_image_to_uint8": [_p, _p, _i64, _p],
     "mmada_image_to_nhwc64_bf16": [_p, _p, _i, _i, _i, _p],
     "mmada_space_to_depth2_bf16": [_p, _p, _i, _i, _i, _i, _p],
+    "mmada_conv1d_gather_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mmada_relu_f32": [_p, _i64, _p],
 }
 
 

@@ -333,3 +333,21 @@ def space_to_depth2(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, H // 2, W // 2, 4 * C), device=x.device, dtype=torch.bfloat16)
     _lib.call("mmada_space_to_depth2_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
     return out
+
+
+def conv1d_gather(x: torch.Tensor, taps: int, dilation: int = 1, upsample: int = 1, relu: bool = False) -> torch.Tensor:
+    """x fp32 [B,T,C] -> bf16 [B, T*upsample, taps*C] (see mmada_conv1d_gather_bf16)."""
+    _chk(x, torch.float32, "x")
+    B, T, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B, T * upsample, taps * C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mmada_conv1d_gather_bf16", x.data_ptr(), out.data_ptr(), B, T, C, taps, dilation, upsample, 1 if relu else 0,
+              _stream())
+    return out
+
+
+def relu_(x: torch.Tensor) -> torch.Tensor:
+    _chk(x, torch.float32, "x")
+    assert x.is_contiguous()
+    _lib.call("mmada_relu_f32", x.data_ptr(), x.numel(), _stream())
+    return x

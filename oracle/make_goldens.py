@@ -235,6 +235,28 @@ def magvit_encoder_case():
           latent_absmax=ref_z.abs().max(), note=np.array("pixels are exactly representable in fp16: feed pixels.float()"))
 
 
+def motion_case():
+    """Motion VQ-VAE decode: the reference's own Decoder class on synthetic weights."""
+    print("[motion decoder]")
+    import sys
+    from . import motion
+    if rb.REF not in sys.path:
+        sys.path.insert(0, rb.REF)
+    from motion_vqvae.models.encdec import Decoder
+    cfg = motion.MOTION
+    sd = motion.make_motion_decoder_weights(0)
+    dec = Decoder(cfg["n_feats"], cfg["code_dim"], cfg["down_t"], 2, cfg["width"], cfg["depth"], cfg["rate"], activation="relu", norm=None).eval()
+    missing, unexpected = dec.load_state_dict({k[len("vqvae.decoder."):]: v for k, v in sd.items() if ".decoder." in k}, strict=True)
+    ids = torch.randint(0, cfg["nb_code"], (1, 49), generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        # vqvae.py:74-81 around the reference's Decoder
+        x_d = torch.nn.functional.embedding(ids, sd["vqvae.quantizer.codebook"]).view(1, -1, cfg["code_dim"]).permute(0, 2, 1).contiguous()
+        ref = dec(x_d).permute(0, 2, 1)
+    mine = motion.forward_decoder(ids, sd)
+    assert torch.equal(ref, mine), "restatement != reference (motion decoder)"
+    _save("motion_decoder", ids=ids, pose=ref, pose_absmax=ref.abs().max())
+
+
 def logits_case(name, cfg, B, L, wseed, seed):
     print(f"[logits] {name}")
     sd = W.make_llada_weights(cfg, wseed)
@@ -259,6 +281,7 @@ def main():
     sampling_case()
     magvit_case()
     magvit_encoder_case()
+    motion_case()
     logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
     logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
     t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)

@@ -116,3 +116,14 @@ def test_magvit_encoder(golden):
         z = magvit.encoder_forward(px, sd)
     assert np.array_equal(z.numpy(), gd["latents"])
     assert np.array_equal(magvit.lfq_bits_to_indices(z.numpy()).reshape(1, -1), gd["codes"])
+
+
+def test_motion_decoder(golden):
+    """Motion VQ-VAE decode: the restatement reproduces the output of the reference's own Decoder class."""
+    from oracle import motion
+    gd = golden("motion_decoder")
+    sd = motion.make_motion_decoder_weights(0)
+    with torch.no_grad():
+        pose = motion.forward_decoder(torch.from_numpy(gd["ids"]), sd)
+    assert pose.shape == (1, 49 * 4, 263)
+    assert np.array_equal(pose.numpy(), gd["pose"])
