@@ -144,6 +144,14 @@ def cpu_sample_seconds(threads, reps, warm=1):
     return tl + tt, 1.0 / sec_per_image
 
 
+def workload_config(world, n_layers, B, L, decode):
+    """BASELINE.json configs[1]; the same dict on both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": "MMaDA-8B-arch t2i 512x512: 1024 image tokens, 15 steps, CFG 3.5, 8 prompts/GPU "
+                        "(16x1539 token rows per forward), random-init bf16 weights",
+            "n_layers": n_layers, "prompts_per_gpu": B, "seq_len": L, "parallelism": f"prompt-shard x{world}",
+            "l2": "inputs_exceed_l2 (16 GB of weights streamed per step)", "decode_in_e2e": decode}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -158,7 +166,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": reps, "warmup": min(args.warmup, 2), "ms_per_step": t_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MMaDA-8B-arch t2i 512x512, 1024 image tokens, 15 steps, CFG 3.5 (CPU, bounded sample)"},
+            "config": workload_config(args.gpus, C2["n_layers"], 8, PREFIX + 1 + N_IMG + 1, True),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -326,10 +334,7 @@ def run_own(args):
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "MMaDA-8B-arch t2i 512x512: 1024 image tokens, 15 steps, CFG 3.5, 8 prompts/GPU "
-                                   "(16x1539 token rows per forward), random-init bf16 weights",
-                       "n_layers": cfgd["n_layers"], "prompts_per_gpu": B, "seq_len": L, "parallelism": f"prompt-shard x{world}",
-                       "l2": "inputs_exceed_l2 (16 GB of weights streamed per step)", "decode_in_e2e": vq is not None},
+            "config": workload_config(world, cfgd["n_layers"], B, L, vq is not None),
             "tokens_per_sec": value * N_IMG, "algorithmic_tflop_per_step": step_tf,
             "model_tflops_per_gpu": step_tf / (ms_step * 1e-3), "frac_of_bf16_sustained_peak": step_tf / (ms_step * 1e-3) / pk["tf_sustained"],
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -81,3 +81,19 @@ def test_interleave_gate_up():
     assert w.shape == (512, 4)
     assert torch.equal(w[:128], g[:128]) and torch.equal(w[128:256], u[:128])
     assert torch.equal(w[256:384], g[128:]) and torch.equal(w[384:], u[128:])
+
+
+def test_torch_custom_ops_registered():
+    """The kernels are also visible to the PyTorch dispatcher (torch.ops.mmada_b200.*), with fake kernels for tracing."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import mmada_b200.torch_ops as t
+    for n in t.OPS:
+        assert hasattr(torch.ops.mmada_b200, n)
+    with FakeTensorMode():
+        a = torch.empty(100, 64, dtype=torch.bfloat16, device="cuda")
+        w = torch.empty(256, 64, dtype=torch.bfloat16, device="cuda")
+        assert torch.ops.mmada_b200.gemm(a, w, 3).shape == (100, 128)           # SwiGLU halves N
+        assert torch.ops.mmada_b200.gemm(a, w, 1).dtype == torch.float32
+        qkv = torch.empty(2 * 77, 3 * 256, dtype=torch.bfloat16, device="cuda")
+        assert torch.ops.mmada_b200.attention(qkv, 2, 77, 4, 64).shape == (154, 256)

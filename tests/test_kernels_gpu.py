@@ -192,3 +192,18 @@ def test_mask_by_random_topk_golden(golden):
     for i, T in enumerate(gd["temperatures"]):
         out = ops.mask_by_random_topk(ml, probs, u, float(T))
         assert torch.equal(out.cpu(), torch.from_numpy(gd["masking"][i]))
+
+
+def test_torch_ops_route_equals_direct_route():
+    """torch.ops.mmada_b200.* (dispatcher) and mmada_b200.ops (ctypes) end in the same launchers."""
+    import mmada_b200.torch_ops  # noqa: F401
+    from mmada_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(300, 512, device="cuda", generator=g).bfloat16()
+    w = torch.randn(768, 512, device="cuda", generator=g).bfloat16()
+    assert torch.equal(torch.ops.mmada_b200.gemm(a, w, ops.EPI_BF16), ops.gemm(a, w, ops.EPI_BF16))
+    x = torch.randn(300, 512, device="cuda", generator=g)
+    wt = torch.rand(512, device="cuda", generator=g)
+    assert torch.equal(torch.ops.mmada_b200.rmsnorm(x, wt, 1e-5), ops.rmsnorm(x, wt, 1e-5))
+    qkv = torch.randn(2 * 150, 3 * 256, device="cuda", generator=g).bfloat16()
+    assert torch.equal(torch.ops.mmada_b200.attention(qkv, 2, 150, 2, 128), ops.attention(qkv, 2, 150, 2, 128))
