@@ -57,7 +57,7 @@ def peaks():
 
 def _ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (not live)."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01b_gemm_traffic.json")
     try:
         return json.load(open(p))["dram_bytes_per_launch_avg"]
     except Exception:

@@ -561,17 +561,21 @@ using namespace mmada;
 // rasterisation / cache-hint defaults, overridable for experiments (MMADA_GEMM_GROUP_M, MMADA_GEMM_HINTS=ab with
 // a,b in {n,f,l} = normal / evict-first / evict-last for the A and B operand loads)
 static void set_tuning(GemmParams& p) {
-    static int group_m = 0;
+    static int group_m = -1;
     static uint64_t ha = kEvictLast, hb = kEvictNormal;   // measured: +2 % sustained vs (8, normal/normal)
-    if (group_m == 0) {
+    if (group_m < 0) {
         const char* g = getenv("MMADA_GEMM_GROUP_M");
-        group_m = g ? atoi(g) : 16;
-        if (group_m < 1) group_m = 16;
+        group_m = g ? atoi(g) : 0;
+        if (group_m < 0) group_m = 0;
         const char* h = getenv("MMADA_GEMM_HINTS");
         auto dec = [](char c) { return c == 'f' ? kEvictFirst : (c == 'l' ? kEvictLast : kEvictNormal); };
         if (h && h[0] && h[1]) { ha = dec(h[0]); hb = dec(h[1]); }
     }
-    p.group_m = group_m; p.hint_a = ha; p.hint_b = hb;
+    // default: 16 m-tiles per group (the A band, 16 x 256 rows x K, stays in L2 while the n-tiles sweep past it);
+    // for long K the band outgrows L2 and a squarer wave re-reads less (profiles/r01b_gemm_traffic_probe.txt:
+    // K = 12288: 3.7 GB at 8 against 4.1 GB at 16; K = 4096: 2.5 GB at 16 against 3.5 GB at 8)
+    p.group_m = group_m ? group_m : (p.K >= 8192 ? 8 : 16);
+    p.hint_a = ha; p.hint_b = hb;
 }
 
 extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
