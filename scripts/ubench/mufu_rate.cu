@@ -35,12 +35,16 @@ __global__ void k(float* out, long long* cyc, int iters) {
                 float a, b;
                 asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x));
                 a = ex2(a); b = ex2(b);
-                if (MODE == 5) {
+                if (MODE >= 5) {
                     uint64_t e;
                     asm volatile("mov.b64 %0, {%1, %2};" : "=l"(e) : "f"(a), "f"(b));
                     asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[2 + (i >> 1)]) : "l"(e));
-                    uint32_t h;
-                    asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+                    uint32_t h = 0;
+                    if (MODE == 5) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+                    if (MODE == 7) {        // integer pack: round half up, take the upper halves (ALU pipe only)
+                        const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+                        asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(h) : "r"(ua), "r"(ub));
+                    }
                     pk ^= h;
                 }
                 v[i] = a - 3.0f; v[i + 1] = b - 3.0f;
@@ -57,9 +61,9 @@ __global__ void k(float* out, long long* cyc, int iters) {
 int main() {
     float* out; long long* cyc;
     cudaMalloc(&out, 4096 * 4); cudaMallocManaged(&cyc, 8);
-    const char* names[6] = {"MUFU.EX2 (ex2.approx.ftz.f32)", "MUFU.RCP", "FFMA2 (fma.rn.f32x2)", "FFMA", "FFMA2 + 2 MUFU.EX2 (per MUFU)", "FFMA2 + 2 MUFU + FADD2 + F2FP (per MUFU)"};
+    const char* names[8] = {"MUFU.EX2 (ex2.approx.ftz.f32)", "MUFU.RCP", "FFMA2 (fma.rn.f32x2)", "FFMA", "FFMA2 + 2 MUFU.EX2 (per MUFU)", "FFMA2 + 2 MUFU + FADD2 + F2FP (per MUFU)", "FFMA2 + 2 MUFU + FADD2 (per MUFU)", "FFMA2 + 2 MUFU + FADD2 + int pack (per MUFU)"};
     const int iters = 2000;
-    for (int mode = 0; mode < 6; ++mode)
+    for (int mode = 0; mode < 8; ++mode)
         for (int wps = 1; wps <= 8; wps *= 2) {      // warps per scheduler
             const int threads = wps * 4 * 32;
             for (int rep = 0; rep < 2; ++rep) {
@@ -69,6 +73,8 @@ int main() {
                 if (mode == 3) k<3><<<1, threads>>>(out, cyc, iters);
                 if (mode == 4) k<4><<<1, threads>>>(out, cyc, iters);
                 if (mode == 5) k<5><<<1, threads>>>(out, cyc, iters);
+                if (mode == 6) k<6><<<1, threads>>>(out, cyc, iters);
+                if (mode == 7) k<7><<<1, threads>>>(out, cyc, iters);
                 cudaDeviceSynchronize();
             }
             const double per = (double)cyc[0] / (iters * 8.0 * wps);       // clocks per warp-instruction per scheduler
