@@ -54,6 +54,32 @@ int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* B, int64_t 
                              const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols,
                              int head_dim, int seq_len, int cta_group, void* stream);
 
+/* ---- RMSNorm folded into the projections around it ------------------------------------------------
+ * RMSLayerNorm.forward (models/modeling_llada.py:315-329) is x * rsqrt(mean(x^2) + eps) * weight in front of the
+ * q|k|v and the ff_proj/up_proj projections (:897-903, :921-924).  Because the projection is linear, the row factor
+ * rsqrt(...) can be applied to the ACCUMULATOR rows and the norm weight multiplied into the projection weight's
+ * columns (done once by the caller), so the normalised activations never travel through HBM:
+ *   producer  mmada_gemm_resid_norm_f32: x fp32 [M,N] += A . B^T (attn_out :724 / ff_out :930 + the residual adds
+ *             :915,:933), and in the same epilogue xb bf16 [M,N] = bf16(x) (the next projection's A operand) and
+ *             ssq_out fp32 [M, N/256] = per 256-column tile, the row's sum of squares; N % 256 == 0.
+ *             mmada_embed_norm_f32 does the same for the embedding rows (ssq_out fp32 [M]).
+ *   consumer  mmada_gemm_swiglu_rownorm_bf16 / mmada_gemm_qkv_rope_rownorm_bf16 = MMADA_EPI_SWIGLU_BF16 /
+ *             mmada_gemm_qkv_rope_bf16 with every accumulator row m scaled by
+ *             rsqrt(sum(row_ssq[m, 0..ssq_tiles)) / norm_dim + eps) first (partials added in index order:
+ *             deterministic).                                                                              */
+int mmada_gemm_resid_norm_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* x, int64_t ldx,
+                              void* xb_bf16, int64_t ld_xb, float* ssq_out, int M, int N, int K, int cta_group,
+                              void* stream);
+int mmada_gemm_swiglu_rownorm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                                   const float* row_ssq, int ssq_tiles, int norm_dim, float eps, int M, int N, int K,
+                                   int cta_group, void* stream);
+int mmada_gemm_qkv_rope_rownorm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                                     const float* sin_table, const float* cos_table, const float* row_ssq,
+                                     int ssq_tiles, int norm_dim, float eps, int M, int N, int K, int rope_cols,
+                                     int head_dim, int seq_len, int cta_group, void* stream);
+int mmada_embed_norm_f32(const int64_t* ids, const void* table_bf16, float* out, void* xb_bf16, float* ssq_out, int M,
+                         int d, int64_t vocab, void* stream);
+
 /* ---- HBM-bound block kernels ----------------------------------------------------------------
  * embed:   out fp32 [M,d] = table bf16 [vocab,d][ids[m]]         models/modeling_llada.py:1222
  * rmsnorm: out bf16 [M_out,d] = x*rsqrt(mean(x^2)+eps)*weight     models/modeling_llada.py:315-329

@@ -22,6 +22,11 @@ SIGNATURES = {
     "mmada_device_arch": [],
     "mmada_gemm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _p],
     "mmada_gemm_qkv_rope_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "mmada_gemm_resid_norm_f32": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p],
+    "mmada_gemm_swiglu_rownorm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _f, _i, _i, _i, _i, _p],
+    "mmada_gemm_qkv_rope_rownorm_bf16": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _i, _i, _f, _i, _i, _i, _i, _i, _i,
+                                         _i, _p],
+    "mmada_embed_norm_f32": [_p, _p, _p, _p, _p, _i, _i, _i64, _p],
     "mmada_embed_f32": [_p, _p, _p, _i, _i, _i64, _p],
     "mmada_rmsnorm_bf16": [_p, _p, _p, _p, _i, _i, _f, _p],
     "mmada_rope_inplace_bf16": [_p, _i64, _p, _p, _i, _i, _i, _i, _p],

@@ -45,6 +45,7 @@ struct AttnParams {
     __nv_bfloat16* out;
     int64_t ldo;
     int L, H, B;
+    int q_begin;           // first query row this launch handles (rows before it belong to another launch)
     float scale_log2;      // softmax scale * log2(e)
 #ifdef MMADA_ATT_TRACE
     long long* trace;      // debug build only: clock64 timeline of CTA 0 (scripts/attn_trace.py)
@@ -101,11 +102,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Cfg::BAR_OFF + 8 * 23);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q_pairs = (p.L + 2 * QT - 1) / (2 * QT);
+    const int q_pairs = (p.L - p.q_begin + 2 * QT - 1) / (2 * QT);
     const int qp = blockIdx.x % q_pairs;
     const int bh = blockIdx.x / q_pairs;
     const int h = bh % p.H, b = bh / p.H;
-    const int q0 = qp * 2 * QT;
+    const int q0 = p.q_begin + qp * 2 * QT;
     const int n_qt = (q0 + QT < p.L) ? 2 : 1;               // second query tile entirely out of range?
     const int n_kv = (p.L + KT - 1) / KT;                   // TMA tiles
     const int T = (p.L + KS - 1) / KS;                      // score sub-tiles
@@ -370,7 +371,7 @@ static long long* g_attn_trace = nullptr;
 
 template <int HD, int POLY>
 static int launch_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
-                            int H, float scale, cudaStream_t stream) {
+                            int H, float scale, int q_begin, cudaStream_t stream) {
     using Cfg = AttnCfg<HD>;
     CUtensorMap mq, mk, mv;
     const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
@@ -390,40 +391,43 @@ static int launch_attention(const void* q, const void* k, const void* v, int64_t
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
     p.L = L; p.H = H; p.B = B;
+    p.q_begin = q_begin;
     p.scale_log2 = scale * 1.4426950408889634f;
 #ifdef MMADA_ATT_TRACE
     p.trace = g_attn_trace;
 #endif
-    const int q_pairs = (L + 2 * QT - 1) / (2 * QT);
+    const int q_pairs = (L - q_begin + 2 * QT - 1) / (2 * QT);
     kern<<<B * H * q_pairs, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(mq, mk, mv, p);
     return cuda_status(cudaGetLastError());
 }
 
-// share of the exponentials on the FMA pipe, in eighths (tuning knob; default set from measurements)
-static int attention_poly_eighths() {
-    static int v = -1;
-    if (v < 0) {
+// share of the exponentials on the FMA pipe, in eighths (tuning knob MMADA_ATT_POLY; -1 = not set: every kernel
+// then uses the default its own measurements gave)
+static int attention_poly_env() {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("MMADA_ATT_POLY");
-        v = e ? atoi(e) : kAttnPolyDefault;
-        if (v != 0 && v != 2 && v != 3 && v != 4) v = kAttnPolyDefault;
+        v = e ? atoi(e) : -1;
+        if (v != 0 && v != 2 && v != 3 && v != 4) v = -1;
     }
     return v;
 }
+static int attention_poly_eighths() { return attention_poly_env() < 0 ? kAttnPolyDefault : attention_poly_env(); }
 
 template <int HD>
 static int dispatch_attention(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
-                              int H, float scale, cudaStream_t stream) {
+                              int H, float scale, int q_begin, cudaStream_t stream) {
     switch (attention_poly_eighths()) {
-        case 0: return launch_attention<HD, 0>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-        case 2: return launch_attention<HD, 2>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-        case 3: return launch_attention<HD, 3>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-        default: return launch_attention<HD, 4>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+        case 0: return launch_attention<HD, 0>(q, k, v, ld, out, ldo, B, L, H, scale, q_begin, stream);
+        case 2: return launch_attention<HD, 2>(q, k, v, ld, out, ldo, B, L, H, scale, q_begin, stream);
+        case 3: return launch_attention<HD, 3>(q, k, v, ld, out, ldo, B, L, H, scale, q_begin, stream);
+        default: return launch_attention<HD, 4>(q, k, v, ld, out, ldo, B, L, H, scale, q_begin, stream);
     }
 }
 
 // attention_pair.cu: persistent CTA pairs, head_dim 128
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
-                          int H, float scale, int poly, cudaStream_t stream);
+                          int Lq, int H, float scale, int poly, cudaStream_t stream);
 
 }  // namespace mmada
 
@@ -447,9 +451,26 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
             const char* e = getenv("MMADA_ATT_PAIR");
             use_pair = e ? atoi(e) != 0 : 1;
         }
-        if (use_pair && L > 128) return launch_attention_pair(q, k, v, ld, out, ldo, B, L, H, scale, attention_poly_eighths(), s);
-        return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+        if (use_pair && L > 128) {
+            // A pair item is 256 query rows.  When the last item of every (batch, head) would hold at most one
+            // 128-row tile (L = 1539: 3 rows), those rows go to the single-CTA kernel instead (one CTA per
+            // (batch, head), a second launch on the same stream) and the pair kernel walks whole items only:
+            // worth it once the extra items would cost the pairs a wave of their own.
+            static int split_tail = -1;     // MMADA_ATT_SPLIT_TAIL=0 disables
+            if (split_tail < 0) {
+                const char* e = getenv("MMADA_ATT_SPLIT_TAIL");
+                split_tail = e ? atoi(e) != 0 : 1;
+            }
+            const int rem = L % 256;
+            if (split_tail && L > 256 && rem > 0 && rem <= 128 && B * H >= num_sms()) {
+                const int st = launch_attention_pair(q, k, v, ld, out, ldo, B, L, L - rem, H, scale, attention_poly_env(), s);
+                if (st) return st;
+                return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, L - rem, s);
+            }
+            return launch_attention_pair(q, k, v, ld, out, ldo, B, L, L, H, scale, attention_poly_env(), s);
+        }
+        return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, 0, s);
     }
-    if (head_dim == 64) return dispatch_attention<64>(q, k, v, ld, out, ldo, B, L, H, scale, s);
+    if (head_dim == 64) return dispatch_attention<64>(q, k, v, ld, out, ldo, B, L, H, scale, 0, s);
     return kUnsupportedShape;
 }

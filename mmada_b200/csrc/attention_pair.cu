@@ -19,13 +19,16 @@
 // has the next score MMA queued behind the current PV.  The epilogue (separate warps) copies O to registers,
 // releases the accumulator and then stores.
 //   warps 0-7    softmax: 16 query rows per warp in the m16n8 fragment layout (a row = one quad of threads);
-//                the two warps of a scheduler alternate between "read scores / max" and "exponentials"
+//                exponentials against a running reference maximum that is only revisited when an exponential
+//                overflows its 2^8 window (read off the partial row sums)
 //   warps 8-11   epilogue: O / l -> bf16, token-major, one thread per query row
 //   warp 12      TMA producer (each CTA loads its halves; full barriers live in the leader CTA)
 //   warp 13      MMA issuer (leader CTA only)
 // TMEM (per CTA): S buffer 0 | S buffer 1 (128 columns each) | P buffer 0 | P buffer 1 (64 each) | O (128).
 #include <math.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "attn_math.cuh"
 #include "common.cuh"
@@ -81,7 +84,7 @@ enum : int {
 };
 static_assert(B_TMEMPTR * 8 + 8 <= 512, "barrier block");
 
-template <int POLY, bool TOKEN>
+template <int POLY, bool MAXCHK>
 __global__ void __launch_bounds__(P_THREADS, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const __grid_constant__ CUtensorMap map_v, const PairParams p) {
@@ -292,17 +295,14 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         // ======================================= softmax =======================================
         // Warp (quarter, sub) owns 16 query rows (TMEM lanes 32 quarter + 16 sub ..+15) and ALL keys of every tile,
         // in the m16n8 fragment layout (tcgen05.ld.16x256b): a row lives in the 4 threads of a quad, 32 scores
-        // each, so the row maximum costs two shuffles and nothing has to cross warps.  The two warps that share
-        // a scheduler (sub 0 / 1 of one quarter) are independent; a token (two named barriers) passed around
-        // the exponential phase keeps them in anti-phase: one warp reads scores and takes maxima while the other
-        // feeds the MUFU pipe (in lock step the pipe idles during every max phase).
+        // each, so a row maximum costs two shuffles and nothing has to cross warps.  The two warps that share a
+        // scheduler (sub 0 / 1 of one quarter) are independent.
         const int quarter = warp & 3, sub = warp >> 2;
         const int q4 = lane & 3;
         const int r0 = quarter * 32 + sub * 16 + (lane >> 2);      // rows r0 and r0 + 8
         const uint32_t lane_off = (uint32_t)(quarter * 32 + sub * 16) << 16;
         const uint32_t pfull_lead = mapa_u32(bar(B_PFULL), 0), sfree_lead = mapa_u32(bar(B_SFREE), 0);
         float* lbuf = reinterpret_cast<float*>(smem + LBUF_OFF);
-        const int tok_wait = 1 + 2 * quarter + sub, tok_pass = 1 + 2 * quarter + (sub ^ 1);
         float m_used[2] = {-INFINITY, -INFINITY}, l_sum[2] = {0.f, 0.f};
         int n = 0, j = 0;
         for (int g = 0; g < G; ++g) {
@@ -351,25 +351,35 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             };
             // exponentials against the reference maxima m_used; P column 4i + q4 holds the bf16 pair of keys
             // (8i + 2 q4, +1): tcgen05.st.16x128b, 64 keys per store.  Returns the thread's partial row sums.
-            auto exp_tile = [&](float (&part)[2]) {
+            // NI = 8-key groups per 64-key half that hold valid keys (8 for whole tiles; the last tile of a
+            // sequence is often a few keys only — L = 1539: 3 — and then skips the exponentials of the padding)
+            float pxm = -INFINITY;      // largest argument handed to the polynomial 2^x (it wraps above 2^128)
+            auto exp_tile_n = [&](float (&part)[2], auto ni_tag) {
+                constexpr int NI = decltype(ni_tag)::value;
                 const float2 nmb2[2] = {make_float2(-m_used[0] * p.scale_log2, -m_used[0] * p.scale_log2),
                                         make_float2(-m_used[1] * p.scale_log2, -m_used[1] * p.scale_log2)};
                 float2 rs2[2][2] = {{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}};
+                pxm = -INFINITY;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    if (hh * 64 < keys16) {
+                    if (hh * 64 < keys16 && (NI == 8 || hh == 0)) {
                         uint32_t pw[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {
-                                const int s0 = 4 * (hh * 8 + i) + 2 * r;
-                                const float2 x = ffma2(make_float2(__uint_as_float(sv[s0]), __uint_as_float(sv[s0 + 1])), sc2, nmb2[r]);
-                                const int u = 2 * i + r;        // 16 pairs per store; spread the polynomial ones evenly
-                                const bool poly = POLY > 0 && ((u + 1) * POLY / 16 != u * POLY / 16);
-                                const float2 e = poly ? ex2_poly2(x) : make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
-                                rs2[r][i & 1] = fadd2(rs2[r][i & 1], e);
-                                pw[2 * i + r] = pack_bf16(e.x, e.y);
+                                if (i < NI) {
+                                    const int s0 = 4 * (hh * 8 + i) + 2 * r;
+                                    const float2 x = ffma2(make_float2(__uint_as_float(sv[s0]), __uint_as_float(sv[s0 + 1])), sc2, nmb2[r]);
+                                    const int u = 2 * i + r;        // 16 pairs per store; spread the polynomial ones evenly
+                                    const bool poly = POLY > 0 && ((u + 1) * POLY / 16 != u * POLY / 16);
+                                    const float2 e = poly ? ex2_poly2(x) : make_float2(ex2_mufu(x.x), ex2_mufu(x.y));
+                                    if (poly && !MAXCHK) pxm = fmaxf(pxm, fmaxf(x.x, x.y));     // FMNMX3
+                                    rs2[r][i & 1] = fadd2(rs2[r][i & 1], e);
+                                    pw[2 * i + r] = pack_bf16(e.x, e.y);
+                                } else {
+                                    pw[2 * i + r] = 0u;
+                                }
                             }
                         }
                         tmem_st_16x128b_x8(t_p + hh * 32, pw);
@@ -378,6 +388,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #pragma unroll
                 for (int r = 0; r < 2; ++r) part[r] = (rs2[r][0].x + rs2[r][0].y) + (rs2[r][1].x + rs2[r][1].y);
             };
+            auto exp_tile = [&](float (&part)[2]) {
+                if (keys16 <= 16) exp_tile_n(part, std::integral_constant<int, 2>{});
+                else if (keys16 <= 32) exp_tile_n(part, std::integral_constant<int, 4>{});
+                else exp_tile_n(part, std::integral_constant<int, 8>{});
+            };
             float mx[2], part[2];
             if (j == 0) {
                 row_max(mx);                                        // first tile of an item: no reference yet
@@ -385,18 +400,35 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 m_used[1] = mx[1];
             }
             if (warp == 0) PTR(0, g, 3);
-            if (TOKEN && (g > 0 || sub == 1)) asm volatile("bar.sync %0, 64;" ::"r"(tok_wait) : "memory");
             // the P buffer of tile g-2 must have been consumed (it has, long ago, unless the tensor pipe is behind)
             if (g >= 2) mbar_wait(bar(B_PVDONE + buf), ((g >> 1) & 1) ^ 1, 33);
             // SPECULATE that the reference maxima still hold (lazy rescale: they do unless a row maximum grows by
-            // more than 2^8): the exponentials start right away and the tile's maxima are taken alongside them (ALU
-            // pipe next to MUFU) instead of in a phase of their own in front.
+            // more than 2^8): the exponentials start right away.  Whether they held is read off the exponentials
+            // themselves — a score more than 2^8 above its reference gives an exponential > 256, hence a partial row
+            // sum > 256 (+inf once it overflows) — so the hot path takes no row maximum at all: no FMNMX chain, no
+            // shuffles (MAXCHK = the previous scheme: tile maxima taken alongside the exponentials, kept for A/B
+            // runs).  The polynomial 2^x wraps for arguments above 128: those are range-checked on their own.
             exp_tile(part);
             if (j != 0) {
-                row_max(mx);
-                const float m_new[2] = {fmaxf(m_used[0], mx[0]), fmaxf(m_used[1], mx[1])};
-                const bool grow[2] = {(m_new[0] - m_used[0]) * p.scale_log2 > 8.0f, (m_new[1] - m_used[1]) * p.scale_log2 > 8.0f};
+                float m_new[2];
+                bool grow[2];
+                if constexpr (MAXCHK) {
+                    row_max(mx);
+                    m_new[0] = fmaxf(m_used[0], mx[0]);
+                    m_new[1] = fmaxf(m_used[1], mx[1]);
+                    grow[0] = (m_new[0] - m_used[0]) * p.scale_log2 > 8.0f;
+                    grow[1] = (m_new[1] - m_used[1]) * p.scale_log2 > 8.0f;
+                } else {
+                    grow[0] = grow[1] = !(part[0] <= 256.0f) || !(part[1] <= 256.0f) || pxm > 120.0f;
+                }
                 if (__any_sync(0xffffffffu, grow[0] || grow[1])) {
+                    if constexpr (!MAXCHK) {            // now the maxima are needed: every row that grew moves its reference
+                        row_max(mx);
+                        m_new[0] = fmaxf(m_used[0], mx[0]);
+                        m_new[1] = fmaxf(m_used[1], mx[1]);
+                        grow[0] = m_new[0] > m_used[0];
+                        grow[1] = m_new[1] > m_used[1];
+                    }
                     // mis-speculated: rescale O and the row sums, redo this tile's exponentials.  The accumulator must
                     // be quiescent: PV(g-1) may still be in flight
                     mbar_wait(bar(B_PVDONE + (buf ^ 1)), ((g - 1) >> 1) & 1, 32);
@@ -424,7 +456,6 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             }
             l_sum[0] += part[0];
             l_sum[1] += part[1];
-            if (TOKEN) asm volatile("bar.arrive %0, 64;" ::"r"(tok_pass) : "memory");
             if (warp == 0) PTR(0, g, 4);
             tmem_st_wait();
             tc_fence_before();
@@ -463,8 +494,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 long long* g_pair_trace = nullptr;
 #endif
 
-template <int POLY, bool TOKEN>
-int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L, int H,
+template <int POLY, bool MAXCHK>
+int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L, int Lq, int H,
                 float scale, cudaStream_t stream) {
     CUtensorMap mq, mk, mv;
     const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)L, (uint64_t)B};
@@ -474,7 +505,7 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
     if ((st = make_tmap(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, q, dims, strides, box128))) return st;
     if ((st = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box64))) return st;
     if ((st = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box128))) return st;
-    auto kern = attention_pair_kernel<POLY, TOKEN>;
+    auto kern = attention_pair_kernel<POLY, MAXCHK>;
     static bool configured = false;
     if (!configured) {
         MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
@@ -484,7 +515,7 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
     p.L = L; p.H = H; p.B = B;
-    p.q_pairs = (L + 255) / 256;
+    p.q_pairs = (Lq + 255) / 256;           // query rows [0, Lq): Lq == L, or a multiple of 256 (the rest: another launch)
     p.items = B * H * p.q_pairs;
     p.scale_log2 = scale * 1.4426950408889634f;
 #ifdef MMADA_ATT_TRACE
@@ -510,25 +541,27 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
 
 }  // namespace
 
-// head_dim 128 entry used by mmada_attention_bf16 (attention.cu); poly = eighths of the exponentials on the FMA pipe
+// head_dim 128 entry used by mmada_attention_bf16 (attention.cu); poly = MMADA_ATT_POLY (share of the exponentials on the
+// FMA pipe), < 0 when not set
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
-                          int H, float scale, int poly, cudaStream_t stream) {
-    static int token = -1;              // MMADA_ATT_TOKEN=1: pass a token between the two warps of a scheduler around the exponentials (A/B runs; measured slower)
-    if (token < 0) {
-        const char* e = getenv("MMADA_ATT_TOKEN");
-        token = e ? atoi(e) != 0 : 0;
+                          int Lq, int H, float scale, int poly, cudaStream_t stream) {
+    static int maxchk = -1;             // MMADA_ATT_MAXCHK=1: take the row maxima of every tile (the previous scheme; A/B runs)
+    if (maxchk < 0) {
+        const char* e = getenv("MMADA_ATT_MAXCHK");
+        maxchk = e ? atoi(e) != 0 : 0;
     }
-    if (token) {
+    if (maxchk) {
         switch (poly) {
-            case 0: return launch_pair<0, true>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-            case 4: return launch_pair<8, true>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-            case 3: return launch_pair<6, true>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-            default: return launch_pair<4, true>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+            case 0: return launch_pair<0, true>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);
+            default: return launch_pair<4, true>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);
         }
     }
+    // default (poly < 0): every exponential on the MUFU pipe — without the row-maximum chain in the hot path the
+    // polynomial's extra FMA-pipe instructions cost more than the MUFU slots they free (0.705 ms against 0.742)
     switch (poly) {
-        case 0: return launch_pair<0, false>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
-        default: return launch_pair<4, false>(q, k, v, ld, out, ldo, B, L, H, scale, stream);
+        case 3: return launch_pair<2, false>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);     // an eighth
+        case 2: case 4: return launch_pair<4, false>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);     // a quarter
+        default: return launch_pair<0, false>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);
     }
 }
 

@@ -42,6 +42,38 @@ __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ 
     }
 }
 
+// ---- embedding gather for the folded-RMSNorm pipeline: also xb bf16 [M, d] (the table row itself = the A operand of
+// the first q|k|v GEMM) and ssq[m] = sum of the row's squares.  One warp per token row.
+__global__ void __launch_bounds__(256) embed_norm_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                                                         float* __restrict__ out, __nv_bfloat16* __restrict__ xb,
+                                                         float* __restrict__ ssq, int M, int d, int64_t vocab) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    int64_t id = ids[m];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint4* src = reinterpret_cast<const uint4*>(table + id * d);
+    uint4* xbr = reinterpret_cast<uint4*>(xb + (int64_t)m * d);
+    float4* o = reinterpret_cast<float4*>(out + (int64_t)m * d);
+    float ss = 0.f;
+    for (int c = lane; c < (d >> 3); c += 32) {
+        const uint4 w = __ldg(src + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+        float4 a, b;
+        float2 t;
+        t = __bfloat1622float2(h[0]); a.x = t.x; a.y = t.y;
+        t = __bfloat1622float2(h[1]); a.z = t.x; a.w = t.y;
+        t = __bfloat1622float2(h[2]); b.x = t.x; b.y = t.y;
+        t = __bfloat1622float2(h[3]); b.z = t.x; b.w = t.y;
+        ss += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w);
+        o[2 * c] = a;
+        o[2 * c + 1] = b;
+        xbr[c] = w;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) ssq[m] = ss;
+}
+
 // ---- RMSNorm: out bf16 [Mo, d] = (x * rsqrt(mean(x^2) + eps)) * w, one warp per row ------------
 // rows != nullptr gathers: output row i is computed from input row rows[i].
 template <int VEC>   // float4 loads per lane; d == 128 * VEC
@@ -157,6 +189,15 @@ extern "C" int mmada_embed_f32(const int64_t* ids, const void* table_bf16, float
     const int cap = num_sms() * 16;
     if (blocks > cap) blocks = cap;
     embed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, (const __nv_bfloat16*)table_bf16, out, M, d, vocab);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int mmada_embed_norm_f32(const int64_t* ids, const void* table_bf16, float* out, void* xb_bf16, float* ssq_out,
+                                    int M, int d, int64_t vocab, void* stream) {
+    if (!ids || !table_bf16 || !out || !xb_bf16 || !ssq_out || M <= 0 || d <= 0) return kBadArgument;
+    if (d % 8) return kUnsupportedShape;
+    embed_norm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, (const __nv_bfloat16*)table_bf16, out,
+                                                                     (__nv_bfloat16*)xb_bf16, ssq_out, M, d, vocab);
     return cuda_status(cudaGetLastError());
 }
 

@@ -47,6 +47,16 @@ struct GemmParams {
     const float* rope_cos;
     int rope_hd, rope_L, rope_cols;          // head dim, sequence length (position = row % L), columns [0, rope_cols) are rotated
     int group_m;                             // rasterisation: tiles walk group_m m-tiles before the next n-tile
+    // RMSNorm folded into the GEMMs around it (models/modeling_llada.py:315-329).  Producer (EPI_RESID_NORM_F32):
+    // besides x (fp32) the epilogue writes bf16(x) = the next GEMM's A operand and, per n-tile, the row's sum of
+    // squares of the 256 new values.  Consumer (row_ssq != nullptr): accumulator rows are scaled by
+    // rsqrt(sum(ssq[row, 0..ssq_tiles)) * ssq_inv_d + ssq_eps); the norm weight is folded into B's columns.
+    __nv_bfloat16* xb_out;
+    int64_t ld_xb;
+    float* ssq_out;                          // [M, num_n_tiles]
+    const float* row_ssq;                    // [M, ssq_tiles]
+    int ssq_tiles;
+    float ssq_inv_d, ssq_eps;
     uint64_t hint_a, hint_b;                 // L2 eviction-priority hints of the operand loads
 };
 
@@ -75,7 +85,8 @@ __device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
 __host__ __device__ constexpr bool epi_has_bias(int e) { return e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_BIAS_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
-__host__ __device__ constexpr bool epi_has_resid(int e) { return e == MMADA_EPI_RESID_F32 || e == MMADA_EPI_BIAS_RESID_F32; }
+constexpr int EPI_RESID_NORM_F32 = 8;     // internal: MMADA_EPI_RESID_F32 + bf16 copy + per-tile row sums of squares
+__host__ __device__ constexpr bool epi_has_resid(int e) { return e == MMADA_EPI_RESID_F32 || e == MMADA_EPI_BIAS_RESID_F32 || e == EPI_RESID_NORM_F32; }
 __host__ __device__ constexpr bool epi_out_bf16(int e) { return e == MMADA_EPI_BF16 || e == MMADA_EPI_BIAS_BF16 || e == MMADA_EPI_SWIGLU_BF16 || e == MMADA_EPI_ROPE_BF16; }
 
 // one 32-column chunk of one accumulator row
@@ -131,9 +142,10 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, int row, int co
 // Transposes a 32-row x ROW_BYTES block (one row per lane, `w` = the lane's row as 32-bit words) through
 // the warp's private staging buffer and writes it with coalesced 16-byte stores: one warp instruction
 // covers 32/PIECES whole rows instead of 16 bytes of 32 different rows.  RESID adds an fp32 residual.
-template <int ROW_BYTES, bool RESID>
+template <int ROW_BYTES, bool RESID, bool NORM = false>
 __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, uint8_t* gptr, const float4* resid,
-                                             int64_t pitch_bytes, int rows_valid, int lane) {
+                                             int64_t pitch_bytes, int rows_valid, int lane, uint8_t* xb_ptr = nullptr,
+                                             int64_t xb_pitch_bytes = 0, float* ssq_acc = nullptr) {
     constexpr int PITCH = ROW_BYTES + 16;        // +16: conflict-free 128-bit accesses in both directions
     constexpr int PIECES = ROW_BYTES / 16;
     constexpr int RPI = 32 / PIECES;
@@ -155,6 +167,11 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t* w, 
                 v.w = __float_as_uint(__uint_as_float(v.w) + b.w);
             }
             *reinterpret_cast<uint4*>(gptr + (int64_t)r * pitch_bytes + piece * 16) = v;
+            if constexpr (NORM) {
+                const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z), d = __uint_as_float(v.w);
+                *reinterpret_cast<uint2*>(xb_ptr + (int64_t)r * xb_pitch_bytes + piece * 8) = make_uint2(pack_bf16(a, b), pack_bf16(c, d));
+                ssq_acc[i] += (a * a + b * b) + (c * c + d * d);
+            }
         }
     }
     __syncwarp();
@@ -358,6 +375,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_wait(tfull_bar(acc), acc_phase, 4);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+            // folded RMSNorm: this lane's accumulator row is scaled by the row's rstd (1 when not in use)
+            [[maybe_unused]] float rs = 1.0f;
+            if constexpr (EPI == MMADA_EPI_SWIGLU_BF16 || EPI == MMADA_EPI_ROPE_BF16) {
+                if (p.row_ssq != nullptr && row < p.M) {
+                    const float* sp = p.row_ssq + (int64_t)row * p.ssq_tiles;
+                    float ss = 0.f;
+                    for (int i = 0; i < p.ssq_tiles; ++i) ss += sp[i];
+                    rs = rsqrtf(ss * p.ssq_inv_d + p.ssq_eps);
+                }
+            }
             if constexpr (EPI == MMADA_EPI_SWIGLU_BF16) {
                 // columns [0,BN/2) = gate, [BN/2,BN) = up for output columns nt*BN/2 + [0,BN/2)
                 uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)nt * (BN / 2) * 2;
@@ -370,8 +397,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     uint32_t w[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        w[j] = pack_bf16(silu_f(__uint_as_float(g[2 * j])) * __uint_as_float(u[2 * j]),
-                                         silu_f(__uint_as_float(g[2 * j + 1])) * __uint_as_float(u[2 * j + 1]));
+                        w[j] = pack_bf16(silu_f(__uint_as_float(g[2 * j]) * rs) * (__uint_as_float(u[2 * j]) * rs),
+                                         silu_f(__uint_as_float(g[2 * j + 1]) * rs) * (__uint_as_float(u[2 * j + 1]) * rs));
                     if (rows_valid > 0) staged_store<64, false>(stage, w, obase + c * 64, nullptr, pitch, rows_valid, lane);
                 }
             } else if constexpr (EPI == MMADA_EPI_ROPE_BF16) {
@@ -390,6 +417,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         tmem_ld_32x32b_x32(t_addr + hh * 128 + 64, hi);
                         tmem_ld_32x32b_x32(t_addr + hh * 128 + 96, hi + 32);
                         tmem_ld_wait();
+                        if (p.row_ssq != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) {
+                                lo[j] = __float_as_uint(__uint_as_float(lo[j]) * rs);
+                                hi[j] = __float_as_uint(__uint_as_float(hi[j]) * rs);
+                            }
+                        }
                         rope_pack<64>(lo, hi, sn, cs, col0 < p.rope_cols);
                         if (rows_valid > 0) {
                             staged_store<128, false>(stage, lo, obase + (int64_t)col0 * 2, nullptr, pitch, rows_valid, lane);
@@ -406,6 +440,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         tmem_ld_32x32b_x32(t_addr + hh * 64, lo);
                         tmem_ld_32x32b_x32(t_addr + hh * 64 + 32, hi);
                         tmem_ld_wait();
+                        if (p.row_ssq != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                lo[j] = __float_as_uint(__uint_as_float(lo[j]) * rs);
+                                hi[j] = __float_as_uint(__uint_as_float(hi[j]) * rs);
+                            }
+                        }
                         rope_pack<32>(lo, hi, sn, cs, col0 < p.rope_cols);
                         if (rows_valid > 0) {   // 64 bytes (low half) then 64 bytes (high half) of the 128-byte head
                             staged_store<64, false>(stage, lo, obase + (int64_t)col0 * 2, nullptr, pitch, rows_valid, lane);
@@ -443,6 +484,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     }
                 }
             } else {
+                [[maybe_unused]] float ssq_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     const int col0 = nt * BN + c * 32;
@@ -457,16 +499,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + col0 + j));
                         }
-                        if (rows_valid > 0)
-                            staged_store<128, epi_has_resid(EPI)>(
-                                stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4, rcur, pitch,
-                                rows_valid, lane);
+                        if constexpr (EPI == EPI_RESID_NORM_F32) {
+                            if (rows_valid > 0)
+                                staged_store<128, true, true>(
+                                    stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4, rcur,
+                                    pitch, rows_valid, lane,
+                                    reinterpret_cast<uint8_t*>(p.xb_out) + ((int64_t)row0 * p.ld_xb + col0) * 2, p.ld_xb * 2, ssq_acc);
+                        } else {
+                            if (rows_valid > 0)
+                                staged_store<128, epi_has_resid(EPI)>(
+                                    stage, v, reinterpret_cast<uint8_t*>(p.out) + (int64_t)row0 * pitch + (int64_t)col0 * 4, rcur, pitch,
+                                    rows_valid, lane);
+                        }
                     } else {
                         store_chunk<EPI>(p, row, col0, v);
                     }
                     if constexpr (epi_has_resid(EPI)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+                    }
+                }
+                if constexpr (EPI == EPI_RESID_NORM_F32) {
+                    // lane holds the partial sums of rows 4 i + (lane >> 3) over its 16-byte pieces: add up the 8
+                    // lanes of a row (fixed order -> deterministic) and publish the tile's share of the row
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float sacc = ssq_acc[i];
+                        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+                        const int r = i * 4 + (lane >> 3);
+                        if ((lane & 7) == 0 && r < rows_valid) p.ssq_out[(int64_t)(row0 + r) * p.num_n_tiles + nt] = sacc;
                     }
                 }
             }
@@ -530,6 +593,7 @@ static int dispatch_gemm256(int epi, const CUtensorMap& ma, const CUtensorMap& m
         case MMADA_EPI_BIAS_F32: return launch_gemm<CG, MMADA_EPI_BIAS_F32, 256, false>(ma, mb, p, s);
         case MMADA_EPI_BIAS_RESID_F32: return launch_gemm<CG, MMADA_EPI_BIAS_RESID_F32, 256, false>(ma, mb, p, s);
         case MMADA_EPI_ROPE_BF16: return launch_gemm<CG, MMADA_EPI_ROPE_BF16, 256, false>(ma, mb, p, s);
+        case EPI_RESID_NORM_F32: return launch_gemm<CG, EPI_RESID_NORM_F32, 256, false>(ma, mb, p, s);
     }
     return kBadArgument;
 }
@@ -578,13 +642,21 @@ static void set_tuning(GemmParams& p) {
     p.hint_a = ha; p.hint_b = hb;
 }
 
-extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
-                               const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
-                               void* stream) {
+// row_ssq / ssq_tiles / norm_dim / eps: folded RMSNorm on the consumer side (SwiGLU epilogue); xb / ld_xb / ssq_out:
+// on the producer side (epilogue EPI_RESID_NORM_F32)
+static int gemm_entry(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo, const void* aux,
+                      const float* bias, int M, int N, int K, int epilogue, int cta_group, void* stream,
+                      const float* row_ssq, int ssq_tiles, int norm_dim, float eps, void* xb, int64_t ld_xb, float* ssq_out) {
     if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return kBadArgument;
     if ((lda % 8) || (ldb % 8) || (K % 8)) return kUnsupportedShape;        // 16-byte global strides for TMA
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return kBadArgument;
-    if (epilogue < 0 || epilogue > MMADA_EPI_BIAS_RESID_F32) return kBadArgument;     // ROPE has its own entry point
+    if (epilogue < 0 || (epilogue > MMADA_EPI_BIAS_RESID_F32 && epilogue != EPI_RESID_NORM_F32)) return kBadArgument;   // ROPE has its own entry point
+    if (epilogue == EPI_RESID_NORM_F32) {
+        if (!xb || !ssq_out) return kBadArgument;
+        if ((N % 256) || (ldo % 4) || (ld_xb % 8)) return kUnsupportedShape;     // whole tiles, vector stores
+        if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(xb)) & 15) return kBadArgument;
+    }
+    if (row_ssq && (epilogue != MMADA_EPI_SWIGLU_BF16 || ssq_tiles <= 0 || norm_dim <= 0)) return kBadArgument;
     if (epilogue == MMADA_EPI_SWIGLU_BF16 && (N % 256)) return kUnsupportedShape;
     if (epi_has_resid(epilogue) && !aux) return kBadArgument;
     if (epi_has_bias(epilogue) && !bias) return kBadArgument;
@@ -601,17 +673,47 @@ extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     p.M = M; p.N = N; p.K = K;
     p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
     p.num_n_tiles = (N + bn - 1) / bn;
+    p.row_ssq = row_ssq; p.ssq_tiles = ssq_tiles; p.ssq_inv_d = norm_dim > 0 ? 1.0f / (float)norm_dim : 0.f; p.ssq_eps = eps;
+    p.xb_out = reinterpret_cast<__nv_bfloat16*>(xb); p.ld_xb = ld_xb; p.ssq_out = ssq_out;
     set_tuning(p);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (narrow) return dispatch_narrow<false>(epilogue, ma, mb, p, s);
     return cta_group == 1 ? dispatch_gemm256<1>(epilogue, ma, mb, p, s) : dispatch_gemm256<2>(epilogue, ma, mb, p, s);
 }
 
+extern "C" int mmada_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                               const void* aux, const float* bias, int M, int N, int K, int epilogue, int cta_group,
+                               void* stream) {
+    if (epilogue > MMADA_EPI_BIAS_RESID_F32) return kBadArgument;
+    return gemm_entry(A, lda, B, ldb, out, ldo, aux, bias, M, N, K, epilogue, cta_group, stream, nullptr, 0, 0, 0.f, nullptr, 0,
+                      nullptr);
+}
+
+// x fp32 [M,N] += A . B^T;  xb bf16 [M,N] = bf16(x);  ssq_out fp32 [M, N/256]: per 256-column tile, the row's sum of x^2
+extern "C" int mmada_gemm_resid_norm_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* x, int64_t ldx,
+                                         void* xb_bf16, int64_t ld_xb, float* ssq_out, int M, int N, int K, int cta_group,
+                                         void* stream) {
+    return gemm_entry(A, lda, B, ldb, x, ldx, x, nullptr, M, N, K, EPI_RESID_NORM_F32, cta_group, stream, nullptr, 0, 0, 0.f,
+                      xb_bf16, ld_xb, ssq_out);
+}
+
+// out bf16 [M,N/2] = silu(r*gate) * (r*up), r[m] = rsqrt(sum(row_ssq[m, 0..ssq_tiles)) / norm_dim + eps): SwiGLU epilogue
+// with the RMSNorm in front of the projection folded in (its weight multiplied into B's columns by the caller)
+extern "C" int mmada_gemm_swiglu_rownorm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                                              const float* row_ssq, int ssq_tiles, int norm_dim, float eps, int M, int N,
+                                              int K, int cta_group, void* stream) {
+    if (!row_ssq) return kBadArgument;
+    return gemm_entry(A, lda, B, ldb, out, ldo, nullptr, nullptr, M, N, K, MMADA_EPI_SWIGLU_BF16, cta_group, stream, row_ssq,
+                      ssq_tiles, norm_dim, eps, nullptr, 0, nullptr);
+}
+
 // Fused q|k|v projection + rotary embedding: out bf16 [M, N] = A . B^T with RoPE applied to the heads inside
 // columns [0, rope_cols) (q and k), position = row % seq_len.
-extern "C" int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
-                                        const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols,
-                                        int head_dim, int seq_len, int cta_group, void* stream) {
+static int qkv_rope_entry(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                          const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols, int head_dim,
+                          int seq_len, int cta_group, void* stream, const float* row_ssq, int ssq_tiles, int norm_dim,
+                          float eps) {
+    if (row_ssq && (ssq_tiles <= 0 || norm_dim <= 0)) return kBadArgument;
     if (!A || !B || !out || !sin_table || !cos_table || M <= 0 || N <= 0 || K <= 0 || seq_len <= 0) return kBadArgument;
     if ((lda % 8) || (ldb % 8) || (K % 8) || (ldo % 8) || (N % 256)) return kUnsupportedShape;
     if ((head_dim != 64 && head_dim != 128) || rope_cols % head_dim || rope_cols > N) return kUnsupportedShape;
@@ -630,10 +732,29 @@ extern "C" int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* 
     p.num_m_tiles = (M + BM * cta_group - 1) / (BM * cta_group);
     p.num_n_tiles = N / 256;
     p.rope_sin = sin_table; p.rope_cos = cos_table; p.rope_hd = head_dim; p.rope_L = seq_len; p.rope_cols = rope_cols;
+    p.row_ssq = row_ssq; p.ssq_tiles = ssq_tiles; p.ssq_inv_d = norm_dim > 0 ? 1.0f / (float)norm_dim : 0.f; p.ssq_eps = eps;
     set_tuning(p);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     return cta_group == 1 ? dispatch_gemm256<1>(MMADA_EPI_ROPE_BF16, ma, mb, p, s)
                           : dispatch_gemm256<2>(MMADA_EPI_ROPE_BF16, ma, mb, p, s);
+}
+
+extern "C" int mmada_gemm_qkv_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out, int64_t ldo,
+                                        const float* sin_table, const float* cos_table, int M, int N, int K, int rope_cols,
+                                        int head_dim, int seq_len, int cta_group, void* stream) {
+    return qkv_rope_entry(A, lda, B, ldb, out, ldo, sin_table, cos_table, M, N, K, rope_cols, head_dim, seq_len, cta_group,
+                          stream, nullptr, 0, 0, 0.f);
+}
+
+// the same with the RMSNorm in front of the projection folded in (see mmada_gemm_swiglu_rownorm_bf16)
+extern "C" int mmada_gemm_qkv_rope_rownorm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* out,
+                                                int64_t ldo, const float* sin_table, const float* cos_table,
+                                                const float* row_ssq, int ssq_tiles, int norm_dim, float eps, int M, int N,
+                                                int K, int rope_cols, int head_dim, int seq_len, int cta_group,
+                                                void* stream) {
+    if (!row_ssq) return kBadArgument;
+    return qkv_rope_entry(A, lda, B, ldb, out, ldo, sin_table, cos_table, M, N, K, rope_cols, head_dim, seq_len, cta_group,
+                          stream, row_ssq, ssq_tiles, norm_dim, eps);
 }
 
 // NHWC convolution as an implicit GEMM: out[b,y,x,co] = bias[co] + sum_{tap,c} in[b,y+dy,x+dx,c] * w[co,tap,c] (+ resid)

@@ -7,7 +7,12 @@ SiLU-gated MLP, no biases, untied output head, no KV cache, fully bidirectional 
 Data layout in HBM (M = batch * seq_len token rows):
   x      fp32 [M, d]        residual stream (fp32 instead of the reference's bf16: costs 2x bytes on a
                             stream read twice per layer, buys margin against the fp32 reference)
-  xn     bf16 [M, d]        RMSNorm output = A operand of the next GEMM
+  xn     bf16 [M, d]        A operand of the q|k|v and gate/up GEMMs.  With the RMSNorm folded into the GEMMs
+                            (``fused_norm``, d % 256 == 0) this is bf16(x), written by the residual GEMM's
+                            epilogue together with per-tile row sums of squares ``ssq`` fp32 [M, d/256]; the
+                            consumer GEMM scales its accumulator rows by rsqrt(mean(x^2)+eps) and the norm
+                            weight is multiplied into the projection weight's columns at load time.
+                            Otherwise: the output of the stand-alone RMSNorm kernel.
   qkv    bf16 [M, 3d]       fused q|k|v projection (weights concatenated at load time), RoPE in place
   att    bf16 [M, d]        attention output, token-major
   h      bf16 [M, ffn]      silu(ff_proj)*up_proj, produced by the GEMM epilogue (weights interleaved)
@@ -75,7 +80,7 @@ class _Layer:
 
 
 class LLaDAModelLM:
-    def __init__(self, config: LLaDAConfig, device="cuda"):
+    def __init__(self, config: LLaDAConfig, device="cuda", fused_norm: Optional[bool] = None):
         self.config = config
         self.device = torch.device(device)
         self.layers: List[_Layer] = []
@@ -86,6 +91,11 @@ class LLaDAModelLM:
         self.cta_group = 2
         #: RoPE in the epilogue of the fused q|k|v GEMM (needs 3*d_model % 256 == 0 and head_dim in {64, 128})
         self.fused_rope = (3 * config.d_model) % 256 == 0 and config.head_dim in (64, 128)
+        #: RMSNorm folded into the GEMMs around it (see the module docstring); fixed before the weights are loaded
+        can_fuse = self.fused_rope and config.d_model % 256 == 0 and config.mlp_hidden_size % 128 == 0
+        if fused_norm and not can_fuse:
+            raise ValueError("fused_norm needs d_model % 256 == 0, mlp_hidden_size % 128 == 0 and head_dim in {64, 128}")
+        self.fused_norm = can_fuse if fused_norm is None else bool(fused_norm)
         self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
 
     # ---- weights ---------------------------------------------------------------------------
@@ -93,8 +103,11 @@ class LLaDAModelLM:
         """``sd`` uses the reference's key names."""
         c, dev = self.config, self.device
 
-        def w(k):
-            return sd[k].to(device=dev, dtype=torch.bfloat16).contiguous()
+        def w(k, norm=None):
+            t = sd[k].to(device=dev)
+            if norm is not None and self.fused_norm:        # fold the preceding RMSNorm's weight into the columns
+                t = t.float() * sd[norm].to(device=dev, dtype=torch.float32)[None, :]
+            return t.to(dtype=torch.bfloat16).contiguous()
 
         def n(k):
             return sd[k].to(device=dev, dtype=torch.float32).contiguous()
@@ -103,9 +116,10 @@ class LLaDAModelLM:
         self.layers = []
         for i in range(c.n_layers):
             b = f"{_P}blocks.{i}."
-            wqkv = torch.cat([w(b + "q_proj.weight"), w(b + "k_proj.weight"), w(b + "v_proj.weight")], 0).contiguous()
-            self.layers.append(_Layer(n(b + "attn_norm.weight"), wqkv, w(b + "attn_out.weight"), n(b + "ff_norm.weight"),
-                                      interleave_gate_up(w(b + "ff_proj.weight"), w(b + "up_proj.weight")),
+            an, fn = b + "attn_norm.weight", b + "ff_norm.weight"
+            wqkv = torch.cat([w(b + "q_proj.weight", an), w(b + "k_proj.weight", an), w(b + "v_proj.weight", an)], 0).contiguous()
+            self.layers.append(_Layer(n(an), wqkv, w(b + "attn_out.weight"), n(fn),
+                                      interleave_gate_up(w(b + "ff_proj.weight", fn), w(b + "up_proj.weight", fn)),
                                       w(b + "ff_out.weight")))
         self.ln_f = n(_P + "ln_f.weight")
         self.head = w(_P + "ff_out.weight")
@@ -151,9 +165,11 @@ class LLaDAModelLM:
         c = self.config
         B, L = input_ids.shape
         sin, cos = self._rope_tables(L)
-        x = ops.embed(input_ids.to(self.device), self.wte)
         M = B * L
         xn = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
+        if self.fused_norm:
+            return self._hidden_states_fused_norm(input_ids, xn, sin, cos)
+        x = ops.embed(input_ids.to(self.device), self.wte)
         qkv = torch.empty((M, 3 * c.d_model), dtype=torch.bfloat16, device=self.device)
         att = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
         h = torch.empty((M, c.mlp_hidden_size), dtype=torch.bfloat16, device=self.device)
@@ -171,6 +187,33 @@ class LLaDAModelLM:
             ops.gemm(xn, ly.w_gate_up, ops.EPI_SWIGLU_BF16, out=h, cta_group=cg)
             ops.gemm(h, ly.ff_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
         self.kernel_launches += 1 + (7 if self.fused_rope else 8) * len(self.layers)
+        return x
+
+    def _hidden_states_fused_norm(self, input_ids, xn, sin, cos):
+        """The block stack with every attn_norm / ff_norm folded into the GEMMs around it: 5 launches per layer
+        (q|k|v+RoPE, attention, attn_out+residual, gate/up+SwiGLU, ff_out+residual)."""
+        c = self.config
+        B, L = input_ids.shape
+        M, d, eps, cg = B * L, c.d_model, c.rms_norm_eps, self.cta_group
+        tiles = d // 256
+        ssq = torch.empty((M, tiles), dtype=torch.float32, device=self.device)
+        qkv = torch.empty((M, 3 * d), dtype=torch.bfloat16, device=self.device)
+        att = torch.empty((M, d), dtype=torch.bfloat16, device=self.device)
+        h = torch.empty((M, c.mlp_hidden_size), dtype=torch.bfloat16, device=self.device)
+        x = ops.embed_norm(input_ids.to(self.device), self.wte, xn, ssq)
+        t_in = 1                                                # the embedding writes one partial per row
+        last = len(self.layers) - 1
+        for i, ly in enumerate(self.layers):
+            ops.gemm_qkv_rope_rownorm(xn, ly.wqkv, sin, cos, d, c.head_dim, L, ssq, t_in, d, eps, out=qkv, cta_group=cg)
+            ops.attention(qkv, B, L, c.n_heads, c.head_dim, out=att)
+            ops.gemm_resid_norm(att, ly.attn_out, x, xn, ssq, cta_group=cg)
+            ops.gemm_swiglu_rownorm(xn, ly.w_gate_up, ssq, tiles, d, eps, out=h, cta_group=cg)
+            if i == last:                                       # ln_f reads the fp32 stream (row-gathered)
+                ops.gemm(h, ly.ff_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
+            else:
+                ops.gemm_resid_norm(h, ly.ff_out, x, xn, ssq, cta_group=cg)
+            t_in = tiles
+        self.kernel_launches += 1 + 5 * len(self.layers)
         return x
 
     @torch.no_grad()

@@ -83,6 +83,88 @@ def gemm_qkv_rope(a: torch.Tensor, wqkv: torch.Tensor, sin: torch.Tensor, cos: t
     return out
 
 
+def _timed(M: int, N: int, K: int, epi: int):
+    """GEMM_EVENTS bracket for the folded-norm GEMM entry points (same record format as gemm())."""
+    ev = GEMM_EVENTS
+    if ev is None:
+        return None, None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0, (e1, M, N, K, epi)
+
+
+def _timed_end(e0, rest):
+    if e0 is not None:
+        rest[0].record()
+        GEMM_EVENTS.append((e0,) + rest)
+
+
+def gemm_resid_norm(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, xb: torch.Tensor, ssq: torch.Tensor,
+                    cta_group: int = 2) -> torch.Tensor:
+    """x fp32 [M,N] += a @ w^T in place; xb bf16 [M,N] = bf16(x); ssq fp32 [M, N/256] = per-tile row sums of x^2
+    (mmada_gemm_resid_norm_f32: the producer half of the folded RMSNorm)."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w"); _chk(x, torch.float32, "x")
+    _chk(xb, torch.bfloat16, "xb"); _chk(ssq, torch.float32, "ssq")
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(1) == 1 and w.stride(1) == 1 and x.shape == (M, N) and xb.shape == (M, N)
+    assert x.stride(1) == 1 and xb.stride(1) == 1 and N % 256 == 0 and ssq.is_contiguous() and ssq.numel() >= M * (N // 256)
+    e0, rest = _timed(M, N, K, EPI_RESID_F32)
+    _lib.call("mmada_gemm_resid_norm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), x.stride(0),
+              xb.data_ptr(), xb.stride(0), ssq.data_ptr(), M, N, K, cta_group, _stream())
+    _timed_end(e0, rest)
+    return x
+
+
+def gemm_swiglu_rownorm(a: torch.Tensor, w: torch.Tensor, ssq: torch.Tensor, ssq_tiles: int, norm_dim: int, eps: float,
+                        out: Optional[torch.Tensor] = None, cta_group: int = 2) -> torch.Tensor:
+    """SwiGLU GEMM whose accumulator rows are scaled by the folded RMSNorm's rstd (mmada_gemm_swiglu_rownorm_bf16)."""
+    _chk(a, torch.bfloat16, "a"); _chk(w, torch.bfloat16, "w"); _chk(ssq, torch.float32, "ssq")
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(1) == 1 and w.stride(1) == 1 and ssq.is_contiguous() and ssq.numel() >= M * ssq_tiles
+    if out is None:
+        out = torch.empty((M, N // 2), dtype=torch.bfloat16, device=a.device)
+    assert out.shape == (M, N // 2) and out.stride(1) == 1
+    e0, rest = _timed(M, N, K, EPI_SWIGLU_BF16)
+    _lib.call("mmada_gemm_swiglu_rownorm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+              out.stride(0), ssq.data_ptr(), ssq_tiles, norm_dim, float(eps), M, N, K, cta_group, _stream())
+    _timed_end(e0, rest)
+    return out
+
+
+def gemm_qkv_rope_rownorm(a: torch.Tensor, wqkv: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, d_model: int,
+                          head_dim: int, seq_len: int, ssq: torch.Tensor, ssq_tiles: int, norm_dim: int, eps: float,
+                          out: Optional[torch.Tensor] = None, cta_group: int = 2) -> torch.Tensor:
+    """gemm_qkv_rope with the folded RMSNorm's row scaling (mmada_gemm_qkv_rope_rownorm_bf16)."""
+    _chk(a, torch.bfloat16, "a"); _chk(wqkv, torch.bfloat16, "wqkv"); _chk(sin, torch.float32, "sin"); _chk(cos, torch.float32, "cos")
+    _chk(ssq, torch.float32, "ssq")
+    M, K = a.shape
+    N = wqkv.shape[0]
+    assert a.stride(1) == 1 and wqkv.stride(1) == 1 and sin.is_contiguous() and cos.is_contiguous()
+    assert sin.shape[-1] == head_dim // 2 and sin.shape[0] >= seq_len and ssq.is_contiguous() and ssq.numel() >= M * ssq_tiles
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    e0, rest = _timed(M, N, K, 7)
+    _lib.call("mmada_gemm_qkv_rope_rownorm_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0),
+              out.data_ptr(), out.stride(0), sin.data_ptr(), cos.data_ptr(), ssq.data_ptr(), ssq_tiles, norm_dim, float(eps),
+              M, N, K, 2 * d_model, head_dim, seq_len, cta_group, _stream())
+    _timed_end(e0, rest)
+    return out
+
+
+def embed_norm(ids: torch.Tensor, table: torch.Tensor, xb: torch.Tensor, ssq: torch.Tensor) -> torch.Tensor:
+    """embed() that also writes the bf16 copy of the rows and their sums of squares (ssq fp32 [M])."""
+    _chk(ids, torch.int64, "ids"); _chk(table, torch.bfloat16, "table"); _chk(xb, torch.bfloat16, "xb"); _chk(ssq, torch.float32, "ssq")
+    ids = ids.contiguous().view(-1)
+    M, d = ids.numel(), table.shape[1]
+    assert xb.shape == (M, d) and xb.is_contiguous() and ssq.numel() >= M
+    out = torch.empty((M, d), dtype=torch.float32, device=ids.device)
+    _lib.call("mmada_embed_norm_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), xb.data_ptr(), ssq.data_ptr(), M, d,
+              table.shape[0], _stream())
+    return out
+
+
 def embed(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     _chk(ids, torch.int64, "ids"); _chk(table, torch.bfloat16, "table")
     ids = ids.contiguous().view(-1)

@@ -119,6 +119,77 @@ def test_gemm_qkv_rope_fused_equals_unfused(hd, H, L, B, cta_group):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("M,d,F,hd", [(777, 512, 1024, 128), (1539 * 2, 1024, 2816, 64), (130, 256, 512, 64)])
+def test_rmsnorm_folded_into_gemms(M, d, F, hd, cta_group):
+    """RMSLayerNorm (models/modeling_llada.py:315-329) folded into the GEMMs around it: the producer epilogue
+    (residual add + bf16 copy + per-tile row sums of squares), then the two consumers (SwiGLU and q|k|v + RoPE with the
+    accumulator rows scaled by rstd) against fp32 torch evaluations of norm -> projection on the same bf16 operands."""
+    from mmada_b200 import ops
+    from mmada_b200.modeling_llada import interleave_gate_up
+    from oracle import llada
+    L = M // 2 if M % 2 == 0 else M
+    eps = 1e-5
+    g = torch.Generator(device="cuda").manual_seed(M + d)
+    a = torch.randn(M, F, device="cuda", generator=g).bfloat16()
+    wo = (torch.randn(d, F, device="cuda", generator=g) / math.sqrt(F)).bfloat16()
+    x0 = torch.randn(M, d, device="cuda", generator=g) * 2
+    # --- producer
+    x = x0.clone()
+    xb = torch.full((M, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    tiles = d // 256
+    ssq = torch.full((M, tiles), float("nan"), device="cuda")
+    ops.gemm_resid_norm(a, wo, x, xb, ssq, cta_group=cta_group)
+    ref_x = ops.gemm(a, wo, ops.EPI_RESID_F32, out=x0.clone(), aux=x0, cta_group=cta_group)
+    assert torch.equal(x, ref_x)                                   # same accumulators, same residual add
+    assert torch.equal(xb, x.bfloat16())
+    ref_ssq = (x.double() ** 2).view(M, tiles, 256).sum(-1)
+    assert _rel(ssq, ref_ssq) < 1e-5
+    x2 = x0.clone()                                                # deterministic: a second run gives the same bits
+    ssq2 = torch.empty_like(ssq)
+    ops.gemm_resid_norm(a, wo, x2, torch.empty_like(xb), ssq2, cta_group=cta_group)
+    assert torch.equal(ssq2, ssq)
+    # --- consumers: norm weight folded into the projection weight's columns
+    wn = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    rstd = torch.rsqrt((x.double() ** 2).mean(-1, keepdim=True) + eps)
+    xn = xb.double() * rstd                                        # what the folded pipeline normalises: bf16(x)
+    wg = (torch.randn(F, d, device="cuda", generator=g) / math.sqrt(d))
+    wu = (torch.randn(F, d, device="cuda", generator=g) / math.sqrt(d))
+    wg_f, wu_f = (wg * wn).bfloat16(), (wu * wn).bfloat16()
+    h = ops.gemm_swiglu_rownorm(xb, interleave_gate_up(wg_f, wu_f), ssq, tiles, d, eps, cta_group=cta_group)
+    ref_h = torch.nn.functional.silu(xn @ wg_f.double().t()) * (xn @ wu_f.double().t())
+    assert _rel(h.double(), ref_h) < 6e-3                          # one bf16 rounding of the result
+    # ... and against the un-folded definition (norm in fp32 on x, bf16 weight product, like the reference)
+    xn_ref = llada.rms_norm(x.cpu(), wn.cpu(), eps).double().cuda()
+    ref_h2 = torch.nn.functional.silu(xn_ref @ wg.bfloat16().double().t()) * (xn_ref @ wu.bfloat16().double().t())
+    assert _rel(h.double(), ref_h2) < 2e-2
+    wqkv = (torch.randn(3 * d, d, device="cuda", generator=g) / math.sqrt(d))
+    wqkv_f = (wqkv * wn).bfloat16()
+    sin, cos = llada.rope_tables(L, hd, 500000.0)
+    sin_h, cos_h = sin[0, 0, :, :hd // 2].contiguous().cuda(), cos[0, 0, :, :hd // 2].contiguous().cuda()
+    qkv = ops.gemm_qkv_rope_rownorm(xb, wqkv_f, sin_h, cos_h, d, hd, L, ssq, tiles, d, eps, cta_group=cta_group)
+    # reference: the explicitly normalised operand through the plain fused q|k|v + RoPE GEMM
+    ref_qkv = ops.gemm_qkv_rope(xn.float().bfloat16(), wqkv_f, sin_h, cos_h, d, hd, L, cta_group=cta_group)
+    assert _rel(qkv.double(), ref_qkv.double()) < 1.5e-2            # two bf16 roundings apart
+    # ssq_tiles = 1 (the embedding's layout): total in column 0
+    tot = ssq.sum(-1).contiguous()
+    qkv1 = ops.gemm_qkv_rope_rownorm(xb, wqkv_f, sin_h, cos_h, d, hd, L, tot, 1, d, eps, cta_group=cta_group)
+    assert _rel(qkv1.double(), qkv.double()) < 1e-2
+
+
+def test_embed_norm():
+    from mmada_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    table = torch.randn(1000, 512, device="cuda", generator=g).bfloat16()
+    ids = torch.randint(0, 1000, (3, 50), device="cuda", generator=g)
+    xb = torch.empty(150, 512, device="cuda", dtype=torch.bfloat16)
+    ssq = torch.empty(150, device="cuda")
+    out = ops.embed_norm(ids, table, xb, ssq)
+    assert torch.equal(out, table[ids.view(-1)].float())
+    assert torch.equal(xb, table[ids.view(-1)])
+    assert _rel(ssq, (out.double() ** 2).sum(-1)) < 1e-6
+
+
 def test_embed():
     from mmada_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -131,7 +202,10 @@ def test_embed():
 @pytest.mark.parametrize("hd", [64, 128], ids=["hd64", "hd128"])
 @pytest.mark.parametrize("B,H,L", [(1, 2, 128), (2, 3, 387), (2, 2, 1539), (1, 1, 100), (1, 2, 256), (1, 1, 257),
                                    # more work items than CTA pairs: the persistent path (buffer reuse, phase flips)
-                                   (2, 40, 700), (3, 60, 130), (5, 32, 1024)])
+                                   (2, 40, 700), (3, 60, 130), (5, 32, 1024),
+                                   # head_dim 128, B*H >= 148 and L % 256 <= 128: whole 256-row items on the pair kernel,
+                                   # the last rows of every (batch, head) on the single-CTA kernel (two launches)
+                                   (5, 32, 1539), (2, 80, 300), (4, 40, 640)])
 def test_attention(hd, B, H, L):
     from mmada_b200 import ops
     d = H * hd

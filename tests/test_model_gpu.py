@@ -17,19 +17,23 @@ class _UP:
     text_tokenizer = _T()
 
 
-def _model(cfg_dict, seed):
+def _model(cfg_dict, seed, fused_norm=None):
     from mmada_b200 import MMadaConfig, MMadaModelLM
     from oracle import weights as W
-    m = MMadaModelLM(MMadaConfig.from_dict(cfg_dict))
+    m = MMadaModelLM(MMadaConfig.from_dict(cfg_dict), fused_norm=fused_norm)
     m.load_state_dict(W.make_llada_weights(cfg_dict, seed))
     return m
 
 
+@pytest.mark.parametrize("fused_norm", [True, False], ids=["norm_folded", "norm_kernel"])
 @pytest.mark.parametrize("name,cfgname,wseed", [("logits_tiny", "TINY", 0), ("logits_tiny128", "TINY128", 1)])
-def test_forward_logits_vs_reference_fp32(golden, name, cfgname, wseed):
+def test_forward_logits_vs_reference_fp32(golden, name, cfgname, wseed, fused_norm):
+    """Both block pipelines — RMSNorm folded into the GEMMs around it (the default) and the stand-alone RMSNorm
+    kernel — against the reference's fp32 logits."""
     from oracle import weights as W
     gd = golden(name)
-    m = _model(getattr(W, cfgname), wseed)
+    m = _model(getattr(W, cfgname), wseed, fused_norm)
+    assert m.fused_norm == fused_norm
     ids = torch.from_numpy(gd["ids"]).cuda()
     lg = m(ids).logits.float().cpu()
     cols = slice(W.TEXT_VOCAB, W.TEXT_VOCAB + W.CODEBOOK)
@@ -42,7 +46,7 @@ def test_forward_logits_vs_reference_fp32(golden, name, cfgname, wseed):
     assert err < TOL
 
 
-@pytest.mark.parametrize("name,cfgname", [("t2i_tiny", "TINY"), ("t2i_tiny128", "TINY128")])
+@pytest.mark.parametrize("name,cfgname", [("t2i_tiny", "TINY"), ("t2i_tiny128", "TINY128"), ("t2i_c1", "C1")])
 def test_t2i_generate_decisions_match_oracle(golden, name, cfgname):
     """Feed the CUDA path's own fp32 logits and the same noise to the CPU oracle step by step: sampled
     ids, masks and the carried state must be bit-identical.  Also reports agreement with the
