@@ -42,6 +42,10 @@ namespace {
 constexpr int P_THREADS = 448;
 constexpr int P_EPI_WARP0 = 8, P_TMA_WARP = 12, P_MMA_WARP = 13;
 constexpr int HD = 128;
+#ifndef MMADA_ATT_SLEEP_NS
+#define MMADA_ATT_SLEEP_NS 200
+#endif
+constexpr unsigned SLEEP_NS = MMADA_ATT_SLEEP_NS;   // poll interval of the warps off the critical path
 constexpr int KST = 4, VST = 4;                     // K / V ring depths
 constexpr int Q_BYTES = 128 * HD * 2;               // 128 query rows (two 64-column boxes of 16 KiB)
 constexpr int K_BYTES = 64 * HD * 2;                // 64 keys (two 64-column boxes of 8 KiB)
@@ -148,7 +152,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             int b, h, q0;
             item_coords(n, b, h, q0);
             const int qb = n & 1;
-            mbar_wait(bar(B_QEMPTY + qb), ((n >> 1) & 1) ^ 1, 10);
+            mbar_wait_backoff(bar(B_QEMPTY + qb), ((n >> 1) & 1) ^ 1, 10, SLEEP_NS);
             if (elect_one()) {
                 if (leader) mbar_arrive_expect_tx(bar(B_QFULL + qb), 2 * Q_BYTES);
                 const int qrow = q0 < p.L ? q0 : 0;               // a tile entirely past the end: any rows, never stored
@@ -160,7 +164,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int j = 0; j < T; ++j) {
                 const int g = n * T + j;
                 const int ks = g % KST, vs = g % VST;
-                mbar_wait(bar(B_KEMPTY + ks), ((g / KST) & 1) ^ 1, 11);
+                mbar_wait_backoff(bar(B_KEMPTY + ks), ((g / KST) & 1) ^ 1, 11, SLEEP_NS);
                 if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(bar(B_KFULL + ks), 2 * K_BYTES);
                     // this CTA's half of the N keys the score MMA covers (N = 128, or tail16 in the last tile)
@@ -170,7 +174,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                                         h * HD + c * 64, j * 128 + (int)rank * half_n, b, kEvictLast);
                 }
                 __syncwarp();
-                mbar_wait(bar(B_VEMPTY + vs), ((g / VST) & 1) ^ 1, 12);
+                mbar_wait_backoff(bar(B_VEMPTY + vs), ((g / VST) & 1) ^ 1, 12, SLEEP_NS);
                 if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(bar(B_VFULL + vs), 2 * V_BYTES);
                     tma_load_3d_2sm(sbase + V_OFF + vs * V_BYTES, &map_v, lbar(B_VFULL + vs), h * HD + (int)rank * 64,
@@ -266,9 +270,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             item_coords(n, b, h, q0);
             const int ob = n & 1;
             const int qrow = q0 + row;
-            mbar_wait(bar(B_LFULL + ob), (n >> 1) & 1, 41);
+            mbar_wait_backoff(bar(B_LFULL + ob), (n >> 1) & 1, 41, 4 * SLEEP_NS);
             const float inv = 1.0f / lbuf[ob * 128 + row];
-            mbar_wait(bar(B_OFULL), n & 1, 40);
+            mbar_wait_backoff(bar(B_OFULL), n & 1, 40, SLEEP_NS);
             tc_fence_after();
             // O -> registers (bf16) first, so that the accumulator is free for the next item before the stores go out
             uint32_t ow[HD / 2];

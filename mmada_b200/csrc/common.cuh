@@ -90,6 +90,28 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, tag);
 }
+// Waits of warps that are off the critical path (epilogue, TMA producer with a deep ring): sleep between polls, so the
+// polling does not compete with the MUFU instructions of the warps that share the scheduler (both go through the
+// MIO queue)
+static __device__ __noinline__ void mbar_wait_backoff_slow(uint32_t bar, uint32_t parity, int tag, unsigned ns) {
+#if MMADA_WATCHDOG
+    long long t0 = clock64();
+    uint32_t n = 0;
+#endif
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+#if MMADA_WATCHDOG
+        if ((++n & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("mmada watchdog: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
+                   (int)blockIdx.x, (int)threadIdx.x, parity);
+            __trap();
+        }
+#endif
+    }
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int tag, unsigned ns) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_backoff_slow(bar, parity, tag, ns);
+}
 // one elected lane of a fully converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -333,6 +355,26 @@ __device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same, carrying a data dependency on 32 registers that an earlier tcgen05.ld fills: their uses cannot be scheduled
+// above the wait when other code sits between the load and the wait (software-pipelined loads)
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x128b_x8(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x128b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
