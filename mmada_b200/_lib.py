@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmada_b200.so")
+#: MMADA_B200_LIB: another build of the same library (A/B runs of kernel variants, scripts/ab_attention.sh)
+LIB_PATH = os.environ.get("MMADA_B200_LIB") or os.path.join(_HERE, "libmmada_b200.so")
 
 _lib: Optional[C.CDLL] = None
 
