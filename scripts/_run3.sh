@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest -x -q -m gpu tests/test_kernels_gpu.py -k "attention" > gpurun_out/t1.log 2>&1; echo "attn tests exit $?"; tail -3 gpurun_out/t1.log
-timeout 120 python scripts/bench_kernels.py --what attn 2>&1 | grep -v "^$"
-MMADA_ATT_SPLIT_TAIL=0 timeout 120 python scripts/attn_trace.py 2>&1 | tee gpurun_out/attn_trace_new.txt | sed -n 18,30p | cut -c1-200
+for v in 10 11 12 13 7 10 12; do printf "variant $v: "; MMADA_SAMPLE_VARIANT=$v timeout 120 python scripts/bench_kernels.py --what sample 2>&1 | grep t2i_sample; done
+for v in 10 12; do MMADA_SAMPLE_VARIANT=$v timeout 300 python -m pytest -x -q -m gpu tests/test_kernels_gpu.py tests/test_model_gpu.py -k "sample or t2i or t2m" 2>&1 | tail -1; done
