@@ -57,8 +57,9 @@ def peaks():
 
 def _ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (not live)."""
-    p = os.path.join(ROOT, "profiles", "r01b_gemm_traffic.json")
-    try:
+    import glob
+    try:        # the latest round's capture (profiles/rNN*_gemm_traffic.json, scripts/summarize_profiles.py)
+        p = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))[-1]
         return json.load(open(p))["dram_bytes_per_launch_avg"]
     except Exception:
         return None
@@ -142,6 +143,53 @@ def cpu_sample_seconds(threads, reps, warm=1):
     tl, tt = sum(t_layer) / len(t_layer), sum(t_tail) / len(t_tail)
     sec_per_image = STEPS_PER_IMAGE * (C2["n_layers"] * tl + tt)
     return tl + tt, 1.0 / sec_per_image
+
+
+def hbm_kernel_rooflines(dev, hbm_peak_gbs, reps=10):
+    """The HBM-bound kernels of the path at config-2 sizes, timed alone with CUDA events after the timed region
+    (operands exceed the 126 MB L2): algorithmic bytes / launch time against the measured copy bandwidth."""
+    from mmada_b200 import ops
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    B, N, C = PROMPTS_PER_GPU, N_IMG, CODEBOOK
+    g = torch.Generator(device=dev).manual_seed(3)
+    cond = torch.randn(B * N, C, device=dev, generator=g)
+    unc = torch.randn(B * N, C, device=dev, generator=g)
+    q = torch.empty(B * N, C, device=dev).exponential_(1, generator=g)
+    u = torch.rand(B, N, device=dev, generator=g)
+    tickets = torch.zeros(B, dtype=torch.int32, device=dev)
+    knowns = [torch.full((B, N), C2["mask_token_id"], dtype=torch.int64, device=dev) for _ in range(reps + 3)]
+    it = iter(knowns)
+    ms = timed(lambda: ops.t2i_sample_step(cond, unc, q, u, next(it), None, 0, tickets, GUIDANCE, 500.0, 0.5,
+                                           C2["mask_token_id"], 126349))
+    nbytes = 3 * B * N * C * 4
+    out["t2i_sample_kernel"] = {"what": "first denoising step: cond + uncond logits + Exp(1) noise of 8 x 1024 masked positions, read once",
+                                "ms": ms, "algorithmic_bytes": nbytes, "achieved": nbytes / ms / 1e6, "peak": hbm_peak_gbs,
+                                "unit": "GB/s", "frac": nbytes / ms / 1e6 / hbm_peak_gbs}
+    del cond, unc, q
+    M, d = 2 * B * (PREFIX + 1 + N_IMG + 1), C2["d_model"]
+    x = torch.randn(M, d, device=dev, generator=g)
+    w = torch.ones(d, device=dev)
+    o = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+    ms = timed(lambda: ops.rmsnorm(x, w, 1e-5, out=o))
+    nbytes = M * d * 6
+    out["rmsnorm_kernel"] = {"what": "16 x 1539 rows x 4096, fp32 in, bf16 out (ln_f runs it on the image rows; the block norms are "
+                                     "folded into the GEMMs)", "ms": ms, "algorithmic_bytes": nbytes,
+                             "achieved": nbytes / ms / 1e6, "peak": hbm_peak_gbs, "unit": "GB/s",
+                             "frac": nbytes / ms / 1e6 / hbm_peak_gbs}
+    return out
 
 
 def workload_config(world, n_layers, B, L, decode):
@@ -319,6 +367,10 @@ def run_own(args):
                 "launches": len(gemm_events), "avg_launch_ms": tot_ms / len(gemm_events),
                 "share_of_step": tot_ms / ms,
                 "per_shape": {k: {"ms": t / n, "tflops": fl / (t / n * 1e-3) / 1e12} for k, (t, n, fl) in by.items()}}
+    try:
+        hbm = hbm_kernel_rooflines(dev, pk["hbm"])
+    except Exception as e:          # secondary numbers must not hide the headline
+        hbm = {"failed": str(e)}
     blk, att, head = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
     step_tf = (blk + att + head) / 1e12
     ms_step = ms / K
@@ -339,7 +391,7 @@ def run_own(args):
             "model_tflops_per_gpu": step_tf / (ms_step * 1e-3), "frac_of_bf16_sustained_peak": step_tf / (ms_step * 1e-3) / pk["tf_sustained"],
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "generations": G},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -41,11 +41,15 @@ def full(tag, what, rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_{what}_ncu_full_raw.csv"), "w").write(raw)
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr = rows[0]
+    hdr, units = rows[0], rows[1]
     out = []
     res = []
     for r in rows[2:]:
         d = {k: r[hdr.index(k)] for k in KEYS if k in hdr}
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):        # to bytes, whatever unit ncu picked for the column
+            if k in hdr:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[hdr.index(k)]]
+                d[k + ".bytes"] = float(r[hdr.index(k)].replace(",", "")) * scale
         d["kernel"] = short(r[hdr.index("Kernel Name")])
         res.append(d)
         out.append(json.dumps(d))
@@ -54,8 +58,35 @@ def full(tag, what, rep):
     return res
 
 
+def traffic(tag, res):
+    """bench.py's roofline.traffic: DRAM bytes per GEMM launch, averaged over the launches of one denoising step
+    (32 layers x {qkv, attn_out, gate_up, ff_out} + the lm_head), from the five captured launches."""
+    M, d, f = 16 * 1539, 4096, 12288
+    alg = {"qkv": 2 * (M * d + 3 * d * d + M * 3 * d), "attn_out": 2 * (M * d + d * d) + 4 * 2 * M * d + 2 * M * d,
+           "gate_up": 2 * (M * d + 2 * f * d + M * f), "ff_out": 2 * (M * f + d * f) + 4 * 2 * M * d + 2 * M * d,
+           "lm_head": 2 * (16384 * d + 8192 * d) + 4 * 16384 * 8192}
+    shapes = {}
+    for r in res:
+        epi = int(re.search(r"gemm_kernel<\d+, (\d+)", r["kernel"]).group(1))
+        ms = float(r["gpu__time_duration.sum"])
+        ms = ms / 1e3 if ms > 50 else ms                                    # us or ms column
+        name = {3: "gate_up", 7: "qkv", 1: "lm_head"}.get(epi) or ("ff_out" if ms > 1.0 else "attn_out")
+        shapes[name] = {"epilogue": epi, "dram_bytes": r["dram__bytes_read.sum.bytes"] + r["dram__bytes_write.sum.bytes"],
+                        "algorithmic_bytes": alg[name], "duration_ms": ms,
+                        "tensor_pipe_active_pct": float(r["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"])}
+    n = 32 * 4 + 1
+    avg = (32 * sum(shapes[k]["dram_bytes"] for k in ("qkv", "attn_out", "gate_up", "ff_out")) + shapes["lm_head"]["dram_bytes"]) / n
+    avg_alg = (32 * sum(alg[k] for k in ("qkv", "attn_out", "gate_up", "ff_out")) + alg["lm_head"]) / n
+    out = {"dram_bytes_per_launch_avg": avg, "algorithmic_bytes_per_launch_avg": avg_alg, "per_shape": shapes,
+           "source": f"ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum) on bench.py --layers 2 --steps 2 --warmup 3, "
+                     f"launches 24..28; profiles/{tag}_gemm_ncu_full_raw.csv; average over the {n} GEMM launches of one "
+                     "denoising step (32 x the four block shapes + the lm_head)"}
+    json.dump(out, open(os.path.join(P, f"{tag}_gemm_traffic.json"), "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     tag, lcsv, grep_, arep = sys.argv[1:5]
     launches(tag, lcsv)
-    full(tag, "gemm", grep_)
+    traffic(tag, full(tag, "gemm", grep_))
     full(tag, "attention_pair", arep)
