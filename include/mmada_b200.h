@@ -91,6 +91,12 @@ int mmada_embed_f32(const int64_t* ids, const void* table_bf16, float* out, int 
                     void* stream);
 int mmada_rmsnorm_bf16(const float* x, const float* weight, void* out_bf16, const int32_t* rows, int M_out,
                        int d, float eps, void* stream);
+/* gather_rows: dst[i, 0..row_bytes) = src[rows[i], 0..row_bytes), any element type (row_bytes, ld_src_bytes multiples of
+ *          16).  Used to restrict the LAST block's attn_out / MLP (models/modeling_llada.py:914-933) to the token rows
+ *          whose logits the caller reads (modeling_mmada.py:167-168 slices the image rows): rows are independent
+ *          after the attention, so the results are bit-identical to running every row.                        */
+int mmada_gather_rows(const void* src, int64_t ld_src_bytes, const int32_t* rows, void* dst, int n_rows, int row_bytes,
+                      void* stream);
 int mmada_rope_inplace_bf16(void* qkv_bf16, int64_t ld, const float* sin_table, const float* cos_table, int M,
                             int d_model, int head_dim, int seq_len, void* stream);
 

@@ -42,6 +42,17 @@ __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ 
     }
 }
 
+// ---- row gather: dst[i, :] = src[rows[i], :], rows of row_bytes (a multiple of 16) bytes, 128-bit copies ----------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restrict__ src, int64_t ld_src16,
+                                                          const int32_t* __restrict__ rows, uint4* __restrict__ dst,
+                                                          int n_rows, int chunks) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n_rows * chunks;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / chunks), c = (int)(i % chunks);
+        dst[i] = __ldcs(src + (int64_t)rows[r] * ld_src16 + c);
+    }
+}
+
 // ---- embedding gather for the folded-RMSNorm pipeline: also xb bf16 [M, d] (the table row itself = the A operand of
 // the first q|k|v GEMM) and ssq[m] = sum of the row's squares.  One warp per token row.
 __global__ void __launch_bounds__(256) embed_norm_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
@@ -189,6 +200,21 @@ extern "C" int mmada_embed_f32(const int64_t* ids, const void* table_bf16, float
     const int cap = num_sms() * 16;
     if (blocks > cap) blocks = cap;
     embed_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, (const __nv_bfloat16*)table_bf16, out, M, d, vocab);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int mmada_gather_rows(const void* src, int64_t ld_src_bytes, const int32_t* rows, void* dst, int n_rows,
+                                 int row_bytes, void* stream) {
+    if (!src || !rows || !dst || n_rows <= 0 || row_bytes <= 0) return kBadArgument;
+    if ((row_bytes % 16) || (ld_src_bytes % 16)) return kUnsupportedShape;
+    if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return kBadArgument;
+    const int chunks = row_bytes / 16;
+    const int64_t work = (int64_t)n_rows * chunks;
+    int blocks = (int)((work + 255) / 256);
+    const int cap = num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, ld_src_bytes / 16, rows, (uint4*)dst,
+                                                                 n_rows, chunks);
     return cuda_status(cudaGetLastError());
 }
 

@@ -96,6 +96,7 @@ class LLaDAModelLM:
         if fused_norm and not can_fuse:
             raise ValueError("fused_norm needs d_model % 256 == 0, mlp_hidden_size % 128 == 0 and head_dim in {64, 128}")
         self.fused_norm = can_fuse if fused_norm is None else bool(fused_norm)
+        self.restrict_last_block = True     # logits_rows(rows=...) runs the last block's attn_out / MLP on those rows only
         self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
 
     # ---- weights ---------------------------------------------------------------------------
@@ -160,21 +161,24 @@ class LLaDAModelLM:
 
     # ---- forward ---------------------------------------------------------------------------
     @torch.no_grad()
-    def hidden_states(self, input_ids: torch.Tensor) -> torch.Tensor:
-        """fp32 residual stream after the last block, [B*L, d] (before ln_f)."""
+    def hidden_states(self, input_ids: torch.Tensor, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 residual stream after the last block (before ln_f): [B*L, d], or [len(rows), d] when ``rows`` (int32
+        indices into the flattened token rows) is given — the last block then runs attn_out and the MLP on those
+        rows only (after the attention every row is independent, so the values are bit-identical)."""
         c = self.config
         B, L = input_ids.shape
         sin, cos = self._rope_tables(L)
         M = B * L
         xn = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
         if self.fused_norm:
-            return self._hidden_states_fused_norm(input_ids, xn, sin, cos)
+            return self._hidden_states_fused_norm(input_ids, xn, sin, cos, rows)
         x = ops.embed(input_ids.to(self.device), self.wte)
         qkv = torch.empty((M, 3 * c.d_model), dtype=torch.bfloat16, device=self.device)
         att = torch.empty((M, c.d_model), dtype=torch.bfloat16, device=self.device)
         h = torch.empty((M, c.mlp_hidden_size), dtype=torch.bfloat16, device=self.device)
         cg = self.cta_group
-        for ly in self.layers:
+        last = len(self.layers) - 1
+        for i, ly in enumerate(self.layers):
             ops.rmsnorm(x, ly.attn_norm, c.rms_norm_eps, out=xn)
             if self.fused_rope:
                 ops.gemm_qkv_rope(xn, ly.wqkv, sin, cos, c.d_model, c.head_dim, L, out=qkv, cta_group=cg)
@@ -182,6 +186,10 @@ class LLaDAModelLM:
                 ops.gemm(xn, ly.wqkv, ops.EPI_BF16, out=qkv, cta_group=cg)
                 ops.rope_inplace(qkv, sin, cos, c.d_model, c.head_dim, L)
             ops.attention(qkv, B, L, c.n_heads, c.head_dim, out=att)
+            if i == last and rows is not None:
+                att, x = ops.gather_rows(att, rows), ops.gather_rows(x, rows)
+                xn, h = xn[:rows.numel()], h[:rows.numel()]
+                self.kernel_launches += 2
             ops.gemm(att, ly.attn_out, ops.EPI_RESID_F32, out=x, aux=x, cta_group=cg)
             ops.rmsnorm(x, ly.ff_norm, c.rms_norm_eps, out=xn)
             ops.gemm(xn, ly.w_gate_up, ops.EPI_SWIGLU_BF16, out=h, cta_group=cg)
@@ -189,7 +197,7 @@ class LLaDAModelLM:
         self.kernel_launches += 1 + (7 if self.fused_rope else 8) * len(self.layers)
         return x
 
-    def _hidden_states_fused_norm(self, input_ids, xn, sin, cos):
+    def _hidden_states_fused_norm(self, input_ids, xn, sin, cos, rows=None):
         """The block stack with every attn_norm / ff_norm folded into the GEMMs around it: 5 launches per layer
         (q|k|v+RoPE, attention, attn_out+residual, gate/up+SwiGLU, ff_out+residual)."""
         c = self.config
@@ -206,6 +214,10 @@ class LLaDAModelLM:
         for i, ly in enumerate(self.layers):
             ops.gemm_qkv_rope_rownorm(xn, ly.wqkv, sin, cos, d, c.head_dim, L, ssq, t_in, d, eps, out=qkv, cta_group=cg)
             ops.attention(qkv, B, L, c.n_heads, c.head_dim, out=att)
+            if i == last and rows is not None:                  # the caller reads these rows only
+                att, x = ops.gather_rows(att, rows), ops.gather_rows(x, rows)
+                xn, h, ssq = xn[:rows.numel()], h[:rows.numel()], ssq[:rows.numel()]
+                self.kernel_launches += 2
             ops.gemm_resid_norm(att, ly.attn_out, x, xn, ssq, cta_group=cg)
             ops.gemm_swiglu_rownorm(xn, ly.w_gate_up, ssq, tiles, d, eps, out=h, cta_group=cg)
             if i == last:                                       # ln_f reads the fp32 stream (row-gathered)
@@ -222,8 +234,10 @@ class LLaDAModelLM:
         """fp32 logits for the token rows ``rows`` (int32 indices into the flattened [B*L] rows; None = all)
         and vocabulary columns [col_lo, col_hi): ln_f and the output head run on those rows only."""
         c = self.config
-        x = self.hidden_states(input_ids)
-        xn = ops.rmsnorm(x, self.ln_f, c.rms_norm_eps, rows=rows)
+        # rows that are a small enough share of the batch also restrict the last block (0.8 % of a config-2 step)
+        early = rows is not None and self.restrict_last_block and 10 * rows.numel() <= 9 * input_ids.numel()
+        x = self.hidden_states(input_ids, rows if early else None)
+        xn = ops.rmsnorm(x, self.ln_f, c.rms_norm_eps, rows=None if early else rows)
         col_hi = c.vocab_size if col_hi is None else col_hi
         self.kernel_launches += 2
         return ops.gemm(xn, self.head[col_lo:col_hi], ops.EPI_F32, cta_group=self.cta_group)

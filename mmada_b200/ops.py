@@ -174,6 +174,16 @@ def embed(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """x[rows] for a 2-D tensor with contiguous rows (any dtype; rows int32)."""
+    _chk(rows, torch.int32, "rows")
+    assert x.dim() == 2 and x.stride(1) == 1 and x.is_cuda
+    out = torch.empty((rows.numel(), x.shape[1]), dtype=x.dtype, device=x.device)
+    _lib.call("mmada_gather_rows", x.data_ptr(), x.stride(0) * x.element_size(), rows.data_ptr(), out.data_ptr(),
+              rows.numel(), x.shape[1] * x.element_size(), _stream())
+    return out
+
+
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, rows: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(x, torch.float32, "x"); _chk(weight, torch.float32, "weight")

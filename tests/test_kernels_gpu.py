@@ -190,6 +190,17 @@ def test_embed_norm():
     assert _rel(ssq, (out.double() ** 2).sum(-1)) < 1e-6
 
 
+def test_gather_rows():
+    from mmada_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for dtype, d in ((torch.float32, 516), (torch.bfloat16, 4096), (torch.bfloat16, 264)):
+        x = torch.randn(700, d, device="cuda", generator=g).to(dtype)
+        rows = torch.randint(0, 700, (333,), device="cuda", generator=g).to(torch.int32)
+        assert torch.equal(ops.gather_rows(x, rows), x[rows.long()])
+        wide = torch.randn(700, 3 * d, device="cuda", generator=g).to(dtype)
+        assert torch.equal(ops.gather_rows(wide[:, d:2 * d], rows), wide[rows.long(), d:2 * d])      # strided source
+
+
 def test_embed():
     from mmada_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(1)

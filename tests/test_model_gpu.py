@@ -46,6 +46,26 @@ def test_forward_logits_vs_reference_fp32(golden, name, cfgname, wseed, fused_no
     assert err < TOL
 
 
+@pytest.mark.parametrize("fused_norm", [True, False], ids=["norm_folded", "norm_kernel"])
+def test_last_block_on_requested_rows_is_bit_identical(fused_norm):
+    """logits_rows(rows=...) gathers the requested token rows after the last block's attention and runs attn_out, the
+    MLP, ln_f and the head on them only: every value must equal the all-rows computation bit for bit."""
+    from oracle import weights as W
+    m = _model(W.TINY128, 1, fused_norm)
+    g = torch.Generator().manual_seed(3)
+    B, L = 3, 200
+    ids = torch.randint(0, 126000, (B, L), generator=g).cuda()
+    rows = torch.cat([torch.arange(b * L + 70, b * L + 170) for b in range(B)]).to(torch.int32).cuda()     # ragged vs tiles
+    n0 = m.kernel_launches
+    some = m.logits_rows(ids, rows, 100, 100 + 1024)
+    n_some = m.kernel_launches - n0
+    m.restrict_last_block = False
+    same = m.logits_rows(ids, rows, 100, 100 + 1024)
+    full = m.logits_rows(ids, None, 100, 100 + 1024)
+    assert n_some == (m.kernel_launches - n0 - n_some) // 2 + 2            # the two gathers
+    assert torch.equal(some, same) and torch.equal(some, full[rows.long()])
+
+
 @pytest.mark.parametrize("name,cfgname", [("t2i_tiny", "TINY"), ("t2i_tiny128", "TINY128"), ("t2i_c1", "C1")])
 def test_t2i_generate_decisions_match_oracle(golden, name, cfgname):
     """Feed the CUDA path's own fp32 logits and the same noise to the CPU oracle step by step: sampled
