@@ -36,19 +36,34 @@ STEPS_PER_IMAGE, N_IMG, PREFIX, CODEBOOK, GUIDANCE, PROMPTS_PER_GPU = 15, 1024, 
 METRIC = "t2i_images_per_sec"
 
 
-def algorithmic_flops_per_step(cfg, B, L, N, C):
+def masked_caps(N=None, T=None):
+    """Upper bound on the still-masked image positions per prompt at every step of a generation (the rows the last
+    block / ln_f / head run on): N, then the previous step's mask_len (mmada_b200/modeling_mmada.py)."""
+    from mmada_b200.sampling import cosine_schedule
+    N, T = N or N_IMG, T or STEPS_PER_IMAGE
+    caps, cap = [], N
+    for s in range(T):
+        caps.append(cap)
+        raw = int(float((N * cosine_schedule(torch.tensor(1.0 * (s + 1) / T))).floor()))
+        cap = max(1, min(cap - 1, raw))
+    return caps
+
+
+def algorithmic_flops_per_step(cfg, B, L, N, C, cap=None):
     """2*m*n*k for every matmul the semantics require: block GEMMs + attention
-    (4*L^2*d per sequence per layer) + lm_head on the N image rows x C codebook columns, both branches.
-    Returns (block, attention, head, not_required): the last block only has to produce the N image rows of every
-    sequence (q, attention rows, attn_out, MLP; k and v are needed for all rows) — `not_required` is what SURVEY's
-    364.69 TFLOP figure counts beyond that; the kernels skip the attn_out / MLP part of it, so the reported
-    algorithmic FLOPs exclude it."""
+    (4*L^2*d per sequence per layer) + lm_head on the image rows x C codebook columns, both branches.
+    Returns (block, attention, head, not_required): the last block only has to produce the `cap` still-masked image
+    rows of every sequence (q, attention rows, attn_out, MLP; k and v are needed for all rows) — `not_required` is what
+    SURVEY's 364.69 TFLOP figure (cap = N, every row through every block) counts beyond that; the kernels skip the
+    attn_out / MLP / head part of it, so the reported algorithmic FLOPs exclude it."""
     d, f, nl = cfg["d_model"], cfg["mlp_hidden_size"], cfg["n_layers"]
-    M, R = 2 * B * L, 2 * B * N
+    cap = N if cap is None else cap
+    M, R = 2 * B * L, 2 * B * cap
     block = 2.0 * M * (4 * d * d + 3 * d * f) * nl
     attn = 4.0 * L * L * d * nl * 2 * B
-    head = 2.0 * R * C * d
-    not_required = 2.0 * (M - R) * (2 * d * d + 3 * d * f) + 4.0 * L * (L - N) * d * 2 * B
+    head = 2.0 * (2 * B * N) * C * d
+    not_required = (2.0 * (M - R) * (2 * d * d + 3 * d * f) + 4.0 * L * (L - cap) * d * 2 * B
+                    + 2.0 * (2 * B * (N - cap)) * C * d)
     return block, attn, head, not_required
 
 
@@ -376,7 +391,10 @@ def run_own(args):
         hbm = hbm_kernel_rooflines(dev, pk["hbm"])
     except Exception as e:          # secondary numbers must not hide the headline
         hbm = {"failed": str(e)}
-    blk, att, head, skip = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
+    blk, att, head, _ = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
+    caps = masked_caps()
+    timed_caps = [caps[i % STEPS_PER_IMAGE] for i in range(K)]             # the K timed steps walk whole generations
+    skip = sum(algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK, c)[3] for c in timed_caps) / K
     step_tf = (blk + att + head - skip) / 1e12
     ms_step = ms / K
     cpu = None

@@ -127,6 +127,21 @@ int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, 
                           int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
                           float one_plus_g, float g, float mask_len_raw, float temperature,
                           int64_t mask_id, int64_t text_vocab, void* stream);
+/* Output head restricted to the still-masked positions (the reference computes the logits of every position and
+ * discards those of known ones, models/modeling_mmada.py:183-184).
+ *   mmada_compact_masked_rows: from known_ids int64 [B,N], rows_out int32 [branches*B*cap] = flattened token rows
+ *     ((r*B + b)*L + img_off + n) of the masked positions of batch row b, cond branch r = 0 then (branches == 2) uncond
+ *     r = 1, padded per row up to `cap` with the row's first image position; slot_out int32 [B,N] = b*cap + j for the
+ *     j-th masked position of row b, -1 for known ones.  `cap` = upper bound on the masked positions per row.
+ *   mmada_t2i_sample_step_compact: mmada_t2i_sample_step on cond/uncond fp32 [B*cap, C] indexed through logit_slot.   */
+int mmada_compact_masked_rows(const int64_t* known_ids, int32_t* rows_out, int32_t* slot_out, int B, int N, int L,
+                              int img_off, int cap, int branches, int64_t mask_id, void* stream);
+int mmada_t2i_sample_step_compact(const float* cond_logits, const float* uncond_logits, const float* q_noise,
+                                  const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
+                                  int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
+                                  int no_remask, int32_t* tickets, int B, int N, int C, float one_plus_g, float g,
+                                  float mask_len_raw, float temperature, int64_t mask_id, int64_t text_vocab,
+                                  const int32_t* logit_slot, void* stream);
 /* masking[b,n] = conf[b,n] < sort(conf[b])[mask_len[b]], conf = log(max(p,1e-20)) + T*gumbel(u).
  * Replaces mask_by_random_topk, models/sampling.py:31-36.                                      */
 int mmada_mask_by_random_topk(const float* probs, const float* u_noise, const int64_t* mask_len,

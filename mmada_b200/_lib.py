@@ -35,6 +35,9 @@ SIGNATURES = {
     "mmada_attention_bf16": [_p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _f, _p],
     "mmada_t2i_sample_step": [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i, _p, _i, _i, _i, _f, _f, _f, _f,
                               _i64, _i64, _p],
+    "mmada_compact_masked_rows": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i64, _p],
+    "mmada_t2i_sample_step_compact": [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i, _p, _i, _i, _i, _f, _f, _f, _f,
+                                      _i64, _i64, _p, _p],
     "mmada_mask_by_random_topk": [_p, _p, _p, _p, _i, _i, _f, _p],
     "mmada_text_sample_rows": [_p, _p, _f, _p, C.c_uint64, _f, _i, _i, _p, _p, _p],
     "mmada_block_mask_count": [_p, _i64, _i, _i, _i, _i64, _p, _p],

@@ -40,6 +40,8 @@ struct T2ISampleParams {
     int64_t* raw_out;       // [B, N]    optional: the raw argmax(p/q) at EVERY position (disables the known-row skip)
     int no_remask;          // 1: commit the merged tokens and skip the re-masking (t2m_generate's last step)
     int32_t* tickets;       // [B]       zero on entry, zero on exit
+    const int32_t* slot;    // [B, N]    optional: row of cond / uncond that holds position (b, n)'s logits (compact logits:
+                            //           only the still-masked positions were given to the output head); nullptr = b*N + n
     int64_t ld_ids;
     int64_t img_off;
     int64_t mask_id;
@@ -145,12 +147,13 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
             p.sel_out[row] = FLT_MAX;
         }
     } else {
-        const float4* c4 = reinterpret_cast<const float4*>(p.cond + (int64_t)row * p.C);
+        const int64_t lrow = p.slot ? max(p.slot[row], 0) : row;     // (a masked position always has a slot: cap bounds them)
+        const float4* c4 = reinterpret_cast<const float4*>(p.cond + lrow * p.C);
         const float4* q4 = reinterpret_cast<const float4*>(p.q + (int64_t)row * p.C);
         float l[VEC][4];
         // ---- CFG mix, CH 128-bit loads per array in flight per thread (register budget: the resident CTAs hide the rest)
         if (p.uncond) {
-            const float4* u4 = reinterpret_cast<const float4*>(p.uncond + (int64_t)row * p.C);
+            const float4* u4 = reinterpret_cast<const float4*>(p.uncond + lrow * p.C);
 #pragma unroll
             for (int i0 = 0; i0 < VEC; i0 += CH) {
                 float4 a[CH], bb[CH];
@@ -276,6 +279,49 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
     if (tid == 0) p.tickets[b] = 0;
 }
 
+// Rows of the still-masked image positions, for the output head restricted to them (north_star; the reference
+// computes and discards the logits of known positions, modeling_mmada.py:183-184).  One CTA per batch row b:
+//   rows[(r*B + b)*cap + j] = (r*B + b)*L + img_off + n_j   for the j-th masked position n_j of row b, r = 0 (cond) and,
+//                             with `branches` = 2, r = 1 (uncond); slots j >= the number of masked positions repeat the
+//                             row's first image position (computed and never read)
+//   slot[b*N + n]           = b*cap + j for masked positions, -1 for known ones
+// `cap` is the caller's upper bound on the masked positions per row (the previous step's mask_len).
+__global__ void __launch_bounds__(256) compact_masked_kernel(const int64_t* __restrict__ known, int32_t* __restrict__ rows,
+                                                             int32_t* __restrict__ slot, int B, int N, int L, int img_off,
+                                                             int cap, int branches, int64_t mask_id) {
+    __shared__ int s_cnt[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int per = (N + 255) / 256;
+    const int n0 = tid * per, n1 = min(N, n0 + per);
+    int c = 0;
+    for (int n = n0; n < n1; ++n) c += known[(int64_t)b * N + n] == mask_id;
+    s_cnt[tid] = c;
+    __syncthreads();
+    if (tid == 0) {                 // exclusive scan of 256 counts
+        int acc = 0;
+        for (int i = 0; i < 256; ++i) { const int v = s_cnt[i]; s_cnt[i] = acc; acc += v; }
+    }
+    __syncthreads();
+    int j = s_cnt[tid];
+    for (int n = n0; n < n1; ++n) {
+        const bool m = known[(int64_t)b * N + n] == mask_id;
+        int sl = -1;
+        if (m && j < cap) {
+            sl = b * cap + j;
+            for (int r = 0; r < branches; ++r) rows[((int64_t)r * B + b) * cap + j] = (r * B + b) * L + img_off + n;
+        }
+        slot[(int64_t)b * N + n] = sl;
+        j += m;
+    }
+    __syncthreads();
+    // total masked = scan value of the last thread + its count; pad the unused slots
+    __shared__ int s_total;
+    if (tid == 255) s_total = j;
+    __syncthreads();
+    for (int k = s_total + tid; k < cap; k += 256)
+        for (int r = 0; r < branches; ++r) rows[((int64_t)r * B + b) * cap + k] = (r * B + b) * L + img_off;
+}
+
 // standalone mask_by_random_topk: masking[b, n] = conf[b, n] < sorted(conf[b])[mask_len[b]]
 __global__ void __launch_bounds__(256) random_topk_kernel(const float* __restrict__ probs, const float* __restrict__ u,
                                                           const int64_t* __restrict__ mask_len, uint8_t* __restrict__ out,
@@ -302,12 +348,24 @@ __global__ void __launch_bounds__(256) random_topk_kernel(const float* __restric
 
 using namespace mmada;
 
-extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, const float* q_noise,
-                                     const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
-                                     int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
-                                     int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
-                                     float one_plus_g, float g, float mask_len_raw, float temperature,
-                                     int64_t mask_id, int64_t text_vocab, void* stream) {
+extern "C" int mmada_compact_masked_rows(const int64_t* known_ids, int32_t* rows_out, int32_t* slot_out, int B, int N,
+                                         int L, int img_off, int cap, int branches, int64_t mask_id, void* stream) {
+    if (!known_ids || !rows_out || !slot_out) return kBadArgument;
+    if (B <= 0 || N <= 0 || cap <= 0 || cap > N || img_off < 0 || img_off + N > L || branches < 1 || branches > 2)
+        return kBadArgument;
+    if ((int64_t)branches * B * L > 0x7fffffffLL) return kUnsupportedShape;
+    compact_masked_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(known_ids, rows_out, slot_out, B, N, L, img_off, cap,
+                                                               branches, mask_id);
+    return cuda_status(cudaGetLastError());
+}
+
+static int t2i_sample_step_impl(const float* cond_logits, const float* uncond_logits, const float* q_noise,
+                                const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
+                                int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
+                                int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
+                                float one_plus_g, float g, float mask_len_raw, float temperature,
+                                int64_t mask_id, int64_t text_vocab, const int32_t* logit_slot, void* stream) {
+    if (logit_slot && raw_out) return kBadArgument;        // raw samples need the logits of every position
     if (!cond_logits || !q_noise || !u_noise || !known_ids || !sampled_out || !sel_out || !tickets) return kBadArgument;
     if (B <= 0 || N <= 0 || N > MAX_TOKENS) return kUnsupportedShape;
     if ((reinterpret_cast<uintptr_t>(cond_logits) | reinterpret_cast<uintptr_t>(uncond_logits) |
@@ -317,6 +375,7 @@ extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* unco
     p.cond = cond_logits; p.uncond = uncond_logits; p.q = q_noise; p.u = u_noise;
     p.known = known_ids; p.input_ids = input_ids; p.sampled_out = sampled_out; p.sel_out = sel_out;
     p.masking_out = masking_out; p.raw_out = raw_out; p.no_remask = no_remask; p.tickets = tickets; p.ld_ids = ld_ids; p.img_off = img_off;
+    p.slot = logit_slot;
     p.mask_id = mask_id; p.text_vocab = text_vocab; p.B = B; p.N = N; p.C = C;
     p.one_plus_g = one_plus_g; p.g = g; p.mask_len_raw = mask_len_raw; p.temperature = temperature;
     cudaStream_t s = (cudaStream_t)stream;
@@ -330,6 +389,30 @@ extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* unco
         default: return kUnsupportedShape;
     }
     return cuda_status(cudaGetLastError());
+}
+
+extern "C" int mmada_t2i_sample_step(const float* cond_logits, const float* uncond_logits, const float* q_noise,
+                                     const float* u_noise, int64_t* known_ids, int64_t* input_ids, int64_t ld_ids,
+                                     int64_t img_off, int64_t* sampled_out, float* sel_out, uint8_t* masking_out,
+                                     int64_t* raw_out, int no_remask, int32_t* tickets, int B, int N, int C,
+                                     float one_plus_g, float g, float mask_len_raw, float temperature,
+                                     int64_t mask_id, int64_t text_vocab, void* stream) {
+    return t2i_sample_step_impl(cond_logits, uncond_logits, q_noise, u_noise, known_ids, input_ids, ld_ids, img_off,
+                                sampled_out, sel_out, masking_out, raw_out, no_remask, tickets, B, N, C, one_plus_g, g,
+                                mask_len_raw, temperature, mask_id, text_vocab, nullptr, stream);
+}
+
+extern "C" int mmada_t2i_sample_step_compact(const float* cond_logits, const float* uncond_logits, const float* q_noise,
+                                             const float* u_noise, int64_t* known_ids, int64_t* input_ids,
+                                             int64_t ld_ids, int64_t img_off, int64_t* sampled_out, float* sel_out,
+                                             uint8_t* masking_out, int no_remask, int32_t* tickets, int B, int N, int C,
+                                             float one_plus_g, float g, float mask_len_raw, float temperature,
+                                             int64_t mask_id, int64_t text_vocab, const int32_t* logit_slot,
+                                             void* stream) {
+    if (!logit_slot) return kBadArgument;
+    return t2i_sample_step_impl(cond_logits, uncond_logits, q_noise, u_noise, known_ids, input_ids, ld_ids, img_off,
+                                sampled_out, sel_out, masking_out, nullptr, no_remask, tickets, B, N, C, one_plus_g, g,
+                                mask_len_raw, temperature, mask_id, text_vocab, logit_slot, stream);
 }
 
 extern "C" int mmada_mask_by_random_topk(const float* probs, const float* u_noise, const int64_t* mask_len,

@@ -96,6 +96,7 @@ class LLaDAModelLM:
         if fused_norm and not can_fuse:
             raise ValueError("fused_norm needs d_model % 256 == 0, mlp_hidden_size % 128 == 0 and head_dim in {64, 128}")
         self.fused_norm = can_fuse if fused_norm is None else bool(fused_norm)
+        self.masked_rows_only = True        # t2i loop: last block + head on the still-masked positions only (modeling_mmada)
         self.restrict_last_block = True     # logits_rows(rows=...) runs the last block's attn_out / MLP on those rows only
         self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
 

@@ -58,15 +58,26 @@ class MMadaModelLM(LLaDAModelLM):
         rows = (torch.arange(R, device=dev, dtype=torch.int32)[:, None] * L + img_off
                 + torch.arange(N, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
         tickets = torch.zeros(B, dtype=torch.int32, device=dev)
+        # The last block, ln_f and the output head run on the STILL-MASKED positions only (the reference computes and
+        # discards the logits of known positions, :183-184).  `cap` bounds the masked positions per row without a host
+        # read: N at the first step (the caller may pass known tokens), then the previous step's mask_len.
+        cap = N
         for step in range(timesteps):
             if stop_after is not None and step >= stop_after:
                 break
             model_input[:B] = input_ids
             if cfg:
                 model_input[B:, P:] = input_ids[:, P:]
-            logits = self.logits_rows(model_input, rows, text_vocab, text_vocab + C)      # [R*N, C] fp32
-            cond = logits[:B * N]
-            unc = logits[B * N:] if cfg else None
+            slot = None
+            if self.masked_rows_only and cap < N:
+                step_rows, slot = ops.compact_masked_rows(known, L, img_off, cap, 2 if cfg else 1, mask_token_id)
+                self.kernel_launches += 1
+            else:
+                step_rows = rows
+            logits = self.logits_rows(model_input, step_rows, text_vocab, text_vocab + C)     # [R*cap, C] fp32
+            half = logits.shape[0] // (2 if cfg else 1)
+            cond = logits[:half]
+            unc = logits[half:] if cfg else None
             if noise is not None:
                 q, u = noise[step]
                 q, u = q.to(dev), u.to(dev)
@@ -86,12 +97,29 @@ class MMadaModelLM(LLaDAModelLM):
             temperature = temperature * (1.0 - ratio)                           # compounding (Q3)
             if u is None:
                 u = torch.zeros((B, N), dtype=torch.float32, device=dev).uniform_(0, 1, generator=generator)
+            if trace is not None and slot is not None:
+                # parity tests replay the step on the CPU oracle with logits at EVERY position: known positions (whose
+                # samples the reference discards) get zeros
+                pos = (slot.view(-1) >= 0).nonzero(as_tuple=True)[0]
+                src = slot.view(-1)[pos].long()
+                full_c = torch.zeros((B * N, C), dtype=torch.float32, device=dev)
+                full_c[pos] = cond[src]
+                full_u = None
+                if unc is not None:
+                    full_u = torch.zeros((B * N, C), dtype=torch.float32, device=dev)
+                    full_u[pos] = unc[src]
             sampled, sel, masking = ops.t2i_sample_step(cond, unc, q, u, known, input_ids, img_off, tickets,
                                                         guidance_scale if cfg else 0.0, mask_len_raw, temperature,
-                                                        mask_token_id, text_vocab, want_masking=trace is not None)
+                                                        mask_token_id, text_vocab, want_masking=trace is not None,
+                                                        slot=slot)
             self.kernel_launches += 1
+            # at most k = max(1, min(unknown - 1, mask_len)) positions stay masked (sampling.cu, modeling_mmada.py:195-200)
+            cap = max(1, min(cap - 1, int(mask_len_raw)))
             if trace is not None:
-                trace.append(dict(step=step, cond=cond.view(B, N, C).clone(), uncond=None if unc is None else unc.view(B, N, C).clone(),
+                if slot is None:
+                    full_c, full_u = cond, unc
+                trace.append(dict(step=step, cond=full_c.view(B, N, C).clone(),
+                                  uncond=None if full_u is None else full_u.view(B, N, C).clone(),
                                   sampled_ids=sampled, selected_probs=sel, masking=masking))
             if caller_ids is not input_ids:
                 caller_ids.copy_(input_ids)                                      # keep the in-place contract

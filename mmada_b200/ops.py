@@ -224,13 +224,19 @@ def attention(qkv: torch.Tensor, batch: int, seq_len: int, n_heads: int, head_di
 def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch.Tensor, u: torch.Tensor,
                     known: torch.Tensor, input_ids: Optional[torch.Tensor], img_off: int, tickets: torch.Tensor,
                     guidance: float, mask_len_raw: float, temperature: float, mask_id: int, text_vocab: int,
-                    want_masking: bool = False, want_raw: bool = False, no_remask: bool = False):
+                    want_masking: bool = False, want_raw: bool = False, no_remask: bool = False,
+                    slot: Optional[torch.Tensor] = None):
     """One fused sampling step (see csrc/sampling.cu).  cond/uncond/q: fp32 [B*N, C]; u fp32 [B, N];
     known int64 [B, N] (updated in place); input_ids int64 [B, L] (image slice updated in place).
     Returns (sampled_ids [B,N] int64, selected_probs [B,N] fp32, masking [B,N] bool or None); with
-    ``want_raw`` a 4th element: the raw samples at every position (t2m_generate's return value)."""
+    ``want_raw`` a 4th element: the raw samples at every position (t2m_generate's return value).
+    ``slot`` (int32 [B, N], from compact_masked_rows): cond/uncond are then [B*cap, C], the logits of the still-masked
+    positions only, and position (b, n) reads row slot[b, n]."""
     B, N = known.shape
     C = cond.shape[-1]
+    if slot is not None:
+        return _t2i_sample_step_compact(cond, uncond, q, u, known, input_ids, img_off, tickets, guidance, mask_len_raw,
+                                        temperature, mask_id, text_vocab, want_masking, no_remask, slot)
     for t, n in ((cond, "cond"), (q, "q"), (u, "u")):
         _chk(t, torch.float32, n)
         assert t.is_contiguous()
@@ -256,6 +262,48 @@ def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch
     if want_raw:
         return sampled, sel, (masking.bool() if want_masking else None), raw
     return sampled, sel, (masking.bool() if want_masking else None)
+
+
+def _t2i_sample_step_compact(cond, uncond, q, u, known, input_ids, img_off, tickets, guidance, mask_len_raw, temperature,
+                             mask_id, text_vocab, want_masking, no_remask, slot):
+    B, N = known.shape
+    C = cond.shape[-1]
+    for t, n in ((cond, "cond"), (q, "q"), (u, "u")):
+        _chk(t, torch.float32, n)
+        assert t.is_contiguous()
+    _chk(known, torch.int64, "known"); _chk(tickets, torch.int32, "tickets"); _chk(slot, torch.int32, "slot")
+    assert known.is_contiguous() and slot.is_contiguous() and slot.numel() == B * N
+    assert q.numel() == B * N * C and u.numel() == B * N and cond.numel() % (B * C) == 0
+    if uncond is not None:
+        _chk(uncond, torch.float32, "uncond")
+        assert uncond.is_contiguous() and uncond.numel() == cond.numel()
+    ld_ids = 0
+    if input_ids is not None:
+        _chk(input_ids, torch.int64, "input_ids")
+        assert input_ids.stride(1) == 1 and input_ids.shape[0] == B
+        ld_ids = input_ids.stride(0)
+    sampled = torch.empty((B, N), dtype=torch.int64, device=cond.device)
+    sel = torch.empty((B, N), dtype=torch.float32, device=cond.device)
+    masking = torch.empty((B, N), dtype=torch.uint8, device=cond.device) if want_masking else None
+    _lib.call("mmada_t2i_sample_step_compact", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
+              _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking),
+              1 if no_remask else 0, tickets.data_ptr(), B, N, C, float(1 + guidance), float(guidance),
+              float(mask_len_raw), float(temperature), mask_id, text_vocab, slot.data_ptr(), _stream())
+    return sampled, sel, (masking.bool() if want_masking else None)
+
+
+def compact_masked_rows(known: torch.Tensor, L: int, img_off: int, cap: int, branches: int, mask_id: int):
+    """(rows int32 [branches*B*cap], slot int32 [B, N]) of the still-masked positions (csrc/sampling.cu,
+    mmada_compact_masked_rows): the token rows to run the last block / ln_f / output head on, and where each
+    position's logits then live."""
+    _chk(known, torch.int64, "known")
+    B, N = known.shape
+    assert known.is_contiguous()
+    rows = torch.empty(branches * B * cap, dtype=torch.int32, device=known.device)
+    slot = torch.empty((B, N), dtype=torch.int32, device=known.device)
+    _lib.call("mmada_compact_masked_rows", known.data_ptr(), rows.data_ptr(), slot.data_ptr(), B, N, L, img_off, cap,
+              branches, mask_id, _stream())
+    return rows, slot
 
 
 def mask_by_random_topk(mask_len: torch.Tensor, probs: torch.Tensor, u: torch.Tensor, temperature: float) -> torch.Tensor:

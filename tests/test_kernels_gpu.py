@@ -295,6 +295,46 @@ def test_t2i_sample_step_bit_exact(B, N, C, guidance):
         torch.testing.assert_close(sel.cpu(), ref["selected_probs"], rtol=2e-6, atol=0)
 
 
+@pytest.mark.parametrize("B,N,C,guidance,frac_known", [(2, 64, 8192, 3.5, 0.3), (3, 100, 512, 2.0, 0.8), (2, 1024, 1024, 0.0, 0.5),
+                                                        (1, 256, 8192, 3.5, 0.0)])
+def test_t2i_sample_step_on_compact_logits(B, N, C, guidance, frac_known):
+    """Logits of the still-masked positions only (compact_masked_rows + slot map) give exactly the step of the full
+    logits; the row list names the masked positions of the cond rows, then the uncond rows, padded per row."""
+    from mmada_b200 import ops
+    cond, unc, q, u, known, ml, temp = _sample_case(B, N, C, guidance, seed=11, frac_known=frac_known)
+    cond, q, u = cond.view(B * N, C).cuda(), q.cuda(), u.cuda()
+    unc = unc.view(B * N, C).cuda() if unc is not None else None
+    tickets = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L, off, mask_id = N + 7, 5, 126336
+    nb = 2 if unc is not None else 1
+    masked = known == mask_id
+    cap = min(N, int(masked.sum(1).max()) + 3)            # an upper bound, with some padding
+    k_full, k_cmp = known.clone().cuda(), known.clone().cuda()
+    rows, slot = ops.compact_masked_rows(k_cmp, L, off, cap, nb, mask_id)
+    rows, slot_h = rows.cpu().view(nb, B, cap), slot.cpu()
+    for b in range(B):
+        pos = masked[b].nonzero().view(-1)
+        assert torch.equal(slot_h[b][pos], b * cap + torch.arange(pos.numel(), dtype=torch.int32))
+        assert bool((slot_h[b][~masked[b]] == -1).all())
+        for r in range(nb):
+            assert torch.equal(rows[r, b, :pos.numel()].long(), (r * B + b) * L + off + pos)
+            assert bool((rows[r, b, pos.numel():] == (r * B + b) * L + off).all())
+    # compact logits: row slot[b, n] holds position (b, n)'s logits, the padding rows garbage
+    sel_pos = (slot.view(-1) >= 0).nonzero().view(-1)
+    c_cmp = torch.full((B * cap, C), 7.0, device="cuda")
+    c_cmp[slot.view(-1)[sel_pos].long()] = cond[sel_pos]
+    u_cmp = None
+    if unc is not None:
+        u_cmp = torch.full((B * cap, C), -3.0, device="cuda")
+        u_cmp[slot.view(-1)[sel_pos].long()] = unc[sel_pos]
+    a = ops.t2i_sample_step(cond, unc, q, u, k_full, None, 0, tickets, guidance, ml, temp, mask_id, 126349, want_masking=True)
+    b_ = ops.t2i_sample_step(c_cmp, u_cmp, q, u, k_cmp, None, 0, tickets, guidance, ml, temp, mask_id, 126349,
+                             want_masking=True, slot=slot)
+    for x, y in zip(a, b_):
+        assert torch.equal(x, y)
+    assert torch.equal(k_full, k_cmp)
+
+
 def test_mask_by_random_topk_golden(golden):
     from mmada_b200 import ops
     gd = golden("sampling")
