@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-for v in 10 11 12 13 7 10 12; do printf "variant $v: "; MMADA_SAMPLE_VARIANT=$v timeout 120 python scripts/bench_kernels.py --what sample 2>&1 | grep t2i_sample; done
-for v in 10 12; do MMADA_SAMPLE_VARIANT=$v timeout 300 python -m pytest -x -q -m gpu tests/test_kernels_gpu.py tests/test_model_gpu.py -k "sample or t2i or t2m" 2>&1 | tail -1; done
+timeout 400 python -m pytest -x -q -m gpu tests/test_kernels_gpu.py -k "attention" > gpurun_out/t1.log 2>&1; echo "attn tests exit $?"; tail -5 gpurun_out/t1.log
+for m in 0 1 2 0 1 2; do printf "tail mode $m: "; MMADA_ATT_TAIL=$m timeout 120 python scripts/bench_kernels.py --what attn 2>&1 | grep "^attention"; done
