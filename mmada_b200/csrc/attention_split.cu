@@ -4,6 +4,12 @@
 // Replaces F.scaled_dot_product_attention(q, k, v, attn_mask=None, is_causal=False) at
 // /root/reference/models/modeling_llada.py:653-660 (no mask is ever applied).
 //
+// STATUS: experimental alternative to attention_pair.cu, selected with MMADA_ATT_SPLIT=1 and parity-tested in a child
+// process (tests/test_kernels_gpu.py::test_attention_split_kernel_variant).  Measured at config 2 (16 x 32 heads,
+// L = 1539): 0.743 ms against 0.686 ms for the pair kernel — the default stays attention_pair.cu (DESIGN.md section 4,
+// lesson 7b has the clock64 breakdown: the agent's chain is exponentials ~2400 clk + hand-over / PV / next-S round trip
+// ~1700 clk, no shorter than the in-phase loop it replaces).
+//
 // Why two agents.  attention_pair.cu gives all 8 softmax warps of a CTA the same score tile: the two warps that share
 // a scheduler run in phase, so every TMEM round trip and every drain of the MUFU pipe (row sums -> overflow vote ->
 // store -> hand-over) is exposed, and the MUFU and tensor pipes both sit at ~50 % (profiles/r01c_attention_pair_*:
@@ -13,7 +19,7 @@
 //     S/P buffer a   (128 TMEM columns: the scores, then — aliased over their first 64 columns — the bf16 probabilities)
 //     accumulator a  (128 TMEM columns) with its own running maximum and row sum
 // so that nothing is shared between the agents and the chain of one agent
-//     S(g) ready -> row max, exponentials, P(g) -> PV(g) -> S(g+2) -> ...
+//     S(g) ready -> exponentials (32 keys at a time, speculating on the running maximum), P(g) -> PV(g) -> S(g+2) -> ...
 // leaves its MUFU slots to the other agent exactly while its own MMAs run: the two warps of a scheduler are in
 // anti-phase by construction.  The epilogue merges the two partial results like split-KV attention:
 //     out = (O_0 2^(m_0 - m) + O_1 2^(m_1 - m)) / (l_0 2^(m_0 - m) + l_1 2^(m_1 - m)),  m = max(m_0, m_1).
@@ -310,10 +316,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
     } else {
         // ======================================= softmax agents =======================================
-        // Agent a = warp / 4 takes the tiles g = a, a+2, ... of the stream; thread = query row (TMEM lane).  Per tile:
-        // pass 1 takes the row maximum (the reference maximum m only moves when it would grow by more than 2^8: lazy
-        // rescale of O_a and l), pass 2 reads the scores again, 32 keys at a time with the next load in flight, and
-        // writes P over the first half of the score columns already consumed.
+        // Agent a = warp / 4 takes the tiles g = a, a+2, ... of the stream; thread = query row (TMEM lane).
         const int a = warp >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
