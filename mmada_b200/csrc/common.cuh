@@ -93,6 +93,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 // Waits of warps that are off the critical path (epilogue, TMA producer with a deep ring): sleep between polls, so the
 // polling does not compete with the MUFU instructions of the warps that share the scheduler (both go through the
 // MIO queue)
+// Blocking wait without a function call (a call into the out-of-line watchdog keeps ptxas from giving the calling region
+// more registers than the kernel-wide cap after setmaxnreg.inc): bounded spin, traps without a message.
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++n > (1u << 26)) __trap();         // each failed try_wait already suspends for a while: seconds in total
+    }
+}
 static __device__ __noinline__ void mbar_wait_backoff_slow(uint32_t bar, uint32_t parity, int tag, unsigned ns) {
 #if MMADA_WATCHDOG
     long long t0 = clock64();
