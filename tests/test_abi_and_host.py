@@ -97,3 +97,35 @@ def test_torch_custom_ops_registered():
         assert torch.ops.mmada_b200.gemm(a, w, 1).dtype == torch.float32
         qkv = torch.empty(2 * 77, 3 * 256, dtype=torch.bfloat16, device="cuda")
         assert torch.ops.mmada_b200.attention(qkv, 2, 77, 4, 64).shape == (154, 256)
+
+
+def test_masked_position_bound_of_the_t2i_loop():
+    """The t2i loop runs the last block / output head on at most `cap` rows per prompt without reading the device:
+    cap = N at the first step, then max(1, min(cap - 1, mask_len)) (mmada_b200/modeling_mmada.py).  Against the oracle's
+    sampling step — random logits, partly known inputs, heavy ties in the confidences — the number of positions that
+    stay masked never exceeds that bound."""
+    import torch
+    from oracle import denoise
+    MASK = 126336
+    for seed, (B, N, C, T, frac_known, ties) in enumerate([(3, 64, 32, 6, 0.0, False), (2, 100, 16, 15, 0.4, False),
+                                                          (2, 48, 8, 5, 0.2, True), (1, 33, 4, 18, 0.9, True)]):
+        g = torch.Generator().manual_seed(seed)
+        known = torch.full((B, N), MASK, dtype=torch.int64)
+        kn = torch.rand(B, N, generator=g) < frac_known
+        known[kn] = torch.randint(0, C, (int(kn.sum()),), generator=g)
+        sched = denoise.t2i_mask_len_schedule(N, T)
+        cap, temperature = N, 1.0
+        for s in range(T):
+            assert int((known == MASK).sum(1).max()) <= cap, (seed, s)
+            logits = torch.randn(B, N, C, generator=g)
+            q = torch.empty(B * N, C).exponential_(1, generator=g)
+            u = torch.rand(B, N, generator=g)
+            if ties:                                        # identical rows and noise: many equal confidences
+                logits[:] = logits[:, :1]
+                q[:] = q[:1]
+                u[:] = 0.5
+            temperature *= 1.0 - (s + 1) / T
+            r = denoise.t2i_sample_step(logits, None, 0.0, known, MASK, sched[s], temperature, q, u)
+            known = r["next_known"]
+            cap = max(1, min(cap - 1, int(sched[s])))
+        assert int((known == MASK).sum(1).max()) <= cap
