@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the MMaDA t2i masked-diffusion denoising path on B200 (BASELINE.json metric).
+"""Benchmark of the MMaDA masked-diffusion denoising path on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]                (own arm; torchrun for N > 1)
   python bench.py --impl reference [--steps K] [--warmup W]          (reference arm: CPU, host cores)
+  python bench.py --config mmu|text|t2m [...]                        (BASELINE configs 3 / 4 / 5, same JSON schema)
 
-A "step" is one denoising step of ``MMadaModelLM.t2i_generate`` on BASELINE configs[1]:
+Default (``--config t2i``): a "step" is one denoising step of ``MMadaModelLM.t2i_generate`` on BASELINE configs[1]:
 MMaDA-8B architecture (32 layers, d=4096, 32 heads, ffn 12288, V=134656), random-init bf16 weights,
 8 synthetic prompts per GPU with CFG 3.5 (16 x 1539 token rows per forward), 1024 image tokens,
 15-step cosine schedule.  K steps are timed as whole generations of 15 steps plus one partial
 generation; images/s = prompts * (K/15) / time.  Prompts are sharded across GPUs (weak scaling,
 8 per GPU), the CFG pair of a prompt stays on one device, no collective inside the loop; the
-end-to-end number adds the host->device copies of the prompts, the token->pixel decode when built,
+end-to-end number adds the host->device copies of the prompts, the token->pixel decode,
 the device->host read of the results and the final NCCL all-gather.
 Prints ONE JSON line (rank 0).
 """
@@ -18,7 +19,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -34,6 +34,7 @@ C2 = dict(d_model=4096, n_heads=32, n_layers=32, mlp_hidden_size=12288, vocab_si
           rms_norm_eps=1e-5, max_sequence_length=4096, mask_token_id=126336)
 STEPS_PER_IMAGE, N_IMG, PREFIX, CODEBOOK, GUIDANCE, PROMPTS_PER_GPU = 15, 1024, 513, 8192, 3.5, 8
 METRIC = "t2i_images_per_sec"
+ROUND = "r02"           # profiles/<ROUND>_* are the captures this round's roofline.traffic / parity_c2 may quote
 
 
 def masked_caps(N=None, T=None):
@@ -75,14 +76,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
-def _ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (not live)."""
-    import glob
-    try:        # the latest round's capture (profiles/rNN*_gemm_traffic.json, scripts/summarize_profiles.py)
-        p = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))[-1]
-        return json.load(open(p))["dram_bytes_per_launch_avg"]
-    except Exception:
-        return None
+def _round_profile(name):
+    """A JSON summary committed under profiles/ for THIS round (profiles/<ROUND>_<name>.json), else None: numbers of an
+    earlier round are never quoted as current."""
+    p = os.path.join(ROOT, "profiles", f"{ROUND}_{name}.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p)), os.path.relpath(p, ROOT)
+        except Exception:
+            return None, None
+    return None, None
 
 
 class ClockSampler:
@@ -129,10 +132,15 @@ class ClockSampler:
 # reference arm / CPU baseline: the oracle restatement (oracle/ — pinned bit-exact to the real
 # reference by oracle/make_goldens.py) timed on the host cores on a bounded sample of the workload
 # ================================================================================================
+CPU_SAMPLE = ("1 of 32 LLaDA-8B blocks on one CFG pair (2x1539 token rows, fp32, oracle port of the reference) + restricted "
+              "head + one sampling step on 1024 image rows; images/s extrapolated x32 layers x15 steps")
+
+
 def cpu_sample_seconds(threads, reps, warm=1):
     """One 8B-architecture LLaDA block on one CFG pair (2 x 1539 token rows, fp32) + the restricted
-    head and one sampling step on its 1024 image rows.  Returns (seconds per sample, images/s)."""
-    from oracle import denoise, llada, weights as W
+    head and one sampling step on its 1024 image rows, `warm` untimed + `reps` timed repetitions.
+    Returns (seconds per sample, images/s extrapolated to the whole 32-layer 15-step generation)."""
+    from oracle import denoise, llada
     torch.set_num_threads(threads)
     cfg = dict(C2, n_layers=1)
     g = torch.Generator().manual_seed(0)
@@ -163,6 +171,136 @@ def cpu_sample_seconds(threads, reps, warm=1):
     tl, tt = sum(t_layer) / len(t_layer), sum(t_tail) / len(t_tail)
     sec_per_image = STEPS_PER_IMAGE * (C2["n_layers"] * tl + tt)
     return tl + tt, 1.0 / sec_per_image
+
+
+def cpu_c1_end_to_end(threads, dev=None, timed=3):
+    """BASELINE configs[0] run END TO END (SURVEY.md 8d / BASELINE.md section 3): reduced LLaDA/MMaDA (4 layers, d=1024),
+    t2i of 256 tokens, 15 steps, CFG 3.5, batch 1, fp32 on the CPU through the oracle port of the reference's loop
+    (full-vocabulary head every step, like the reference), 1 warm-up + `timed` timed runs; and the same configuration
+    through mmada_b200 on the GPU beside it."""
+    from oracle import denoise, llada, weights as W
+    torch.set_num_threads(threads)
+    cfg = W.C1
+    sd = W.make_llada_weights(cfg, 0)
+    P, N = 129, 256
+    cond, unc, _, _ = W.make_t2i_prompts(1, P, N, 1)
+    g = torch.Generator().manual_seed(5)
+    noise = [(torch.empty(N, W.CODEBOOK).exponential_(1, generator=g), torch.rand(1, N, generator=g))
+             for _ in range(STEPS_PER_IMAGE)]
+    ts = []
+    with torch.no_grad():
+        for r in range(1 + timed):
+            t0 = time.perf_counter()
+            denoise.t2i_generate(lambda ids: llada.forward_logits(ids, sd, cfg), cond.clone(), unc.clone(),
+                                 guidance_scale=GUIDANCE, timesteps=STEPS_PER_IMAGE, seq_len=N, resolution=P - 1,
+                                 text_vocab=W.TEXT_VOCAB, noise=noise)
+            if r:
+                ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    out = {"what": "BASELINE configs[0] end to end: 4 layers, d=1024, 16 heads, ffn 2816, 256 image tokens, 15 steps, CFG 3.5, "
+                   "batch 1, L=387, fp32, full-vocabulary head (oracle port of the reference loop), 1 warm-up + "
+                   f"{timed} timed", "cores": threads, "kind": "port", "cpu_images_per_s": 1.0 / sec,
+           "cpu_ms_per_step": sec / STEPS_PER_IMAGE * 1e3}
+    if dev is not None:
+        from mmada_b200 import MMadaConfig, MMadaModelLM
+        from mmada_b200.prompting import UniPromptingLike
+        m = MMadaModelLM(MMadaConfig.from_dict(cfg), device=dev).load_state_dict(sd)
+        up = UniPromptingLike(W.TEXT_VOCAB)
+        noise_d = [(q.to(dev), u.to(dev)) for q, u in noise]
+        unc_d = unc.to(dev)
+
+        def run():
+            return m.t2i_generate(input_ids=cond.clone().to(dev), uncond_input_ids=unc_d, guidance_scale=GUIDANCE,
+                                  timesteps=STEPS_PER_IMAGE, seq_len=N, resolution=P - 1, uni_prompting=up, noise=noise_d)
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(timed):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / timed
+        out.update(gpu_images_per_s=1e3 / ms, gpu_ms_per_step=ms / STEPS_PER_IMAGE,
+                   gpu_note="same weights, prompts and noise through mmada_b200 (bf16) on one B200; launch-latency bound at "
+                            "this size (774 token rows)")
+        del m
+    return out
+
+
+def library_baseline(dev, reps=5):
+    """The reference's OWN GPU code path on this B200, outside the product: its LLaDA block is nn.Linear (cuBLAS bf16),
+    F.scaled_dot_product_attention (flash / cuDNN), eager RMSNorm / RoPE / SiLU (models/modeling_llada.py:886-934).
+    One block at config-2 size (16 x 1539 token rows, bf16, plain torch written out here — nothing of mmada_b200 or
+    oracle/ involved) timed with CUDA events and extrapolated x32, plus the reference's full-vocabulary head
+    (134656 columns on all 24624 rows, modeling_llada.py:1356-1362).  The eager sampling chain, the attention-bias
+    build and host syncs of the reference loop are NOT included: a lower bound on the reference's GPU step."""
+    import torch.nn.functional as F
+    d, f, H = C2["d_model"], C2["mlp_hidden_size"], C2["n_heads"]
+    B2, L = 2 * PROMPTS_PER_GPU, PREFIX + 1 + N_IMG + 1
+    g = torch.Generator(device=dev).manual_seed(1)
+
+    def w(o, i):
+        return (torch.randn(o, i, device=dev, generator=g) * i ** -0.5).bfloat16()
+
+    wq, wk, wv, wo, wg, wu, wd = w(d, d), w(d, d), w(d, d), w(d, d), w(f, d), w(f, d), w(d, f)
+    n1 = n2 = torch.ones(d, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(B2, L, d, device=dev, generator=g).bfloat16()
+    hd = d // H
+    inv = 1.0 / (C2["rope_theta"] ** (torch.arange(0, hd, 2, device=dev, dtype=torch.float) / hd))
+    fr = torch.einsum("i,j->ij", torch.arange(L, device=dev, dtype=torch.float), inv)
+    pos = torch.cat((fr, fr), -1)
+    sin, cos = pos.sin()[None, None], pos.cos()[None, None]
+
+    def rms(t, wt):
+        tf = t.float()
+        return wt * (tf * torch.rsqrt(tf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(t.dtype)
+
+    def rot(t):
+        t = t.view(*t.shape[:-1], 2, hd // 2)
+        a, b = t.unbind(-2)
+        return torch.cat((-b, a), -1)
+
+    def rope(t):
+        tf = t.float()
+        return (tf * cos + rot(tf) * sin).to(t.dtype)
+
+    def block(x):
+        h = rms(x, n1)
+        q, k, v = (F.linear(h, m).view(B2, L, H, hd).transpose(1, 2) for m in (wq, wk, wv))
+        a = F.scaled_dot_product_attention(rope(q), rope(k), v).transpose(1, 2).reshape(B2, L, d)
+        x = x + F.linear(a, wo)
+        h = rms(x, n2)
+        return x + F.linear(F.silu(F.linear(h, wg)) * F.linear(h, wu), wd)
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    with torch.no_grad():
+        ms_block = timed(lambda: block(x), reps)
+        q = torch.randn(B2, H, L, hd, device=dev, generator=g).bfloat16()
+        ms_sdpa = timed(lambda: F.scaled_dot_product_attention(q, q, q), reps)
+        del q
+        head = w(8192, d)
+        ms_head_sliced = timed(lambda: F.linear(x[:, -(N_IMG + 1):-1], head), reps)
+        # the reference's full-vocabulary head: 24624 x 134656 bf16 = 6.6 GB of logits; timed in 8192-column slices
+        ms_head_full = ms_head_sliced * (2 * PROMPTS_PER_GPU * L * C2["vocab_size"]) / (2 * PROMPTS_PER_GPU * N_IMG * 8192)
+    ms_step = C2["n_layers"] * ms_block + ms_head_full
+    return {"what": "reference's GPU library path on the same B200 (torch bf16: cuBLAS nn.Linear + SDPA + eager norm/rope/silu), one "
+                    "block of 16x1539 rows timed and extrapolated x32 + full-vocabulary head (scaled from an 8192-column slice); "
+                    "sampling chain / bias build / host syncs excluded (lower bound on the reference's GPU step)",
+            "ms_per_block": ms_block, "ms_sdpa_16x32x1539x128": ms_sdpa, "ms_head_full_vocab_est": ms_head_full,
+            "ms_per_step": ms_step, "images_per_s": PROMPTS_PER_GPU / (ms_step * STEPS_PER_IMAGE / 1e3),
+            "torch": torch.__version__}
 
 
 def hbm_kernel_rooflines(dev, hbm_peak_gbs, reps=10):
@@ -221,22 +359,29 @@ def workload_config(world, n_layers, B, L, decode):
 
 
 def run_reference(args):
+    """Reference arm: `--warmup W` untimed and `--steps K` timed repetitions of the bounded CPU sample; `steps` and `warmup`
+    are reported as passed.  One repetition is NOT a whole denoising step (that is ~15 min on these cores): ms_per_step
+    is the extrapolated time of one (32 blocks + head + sampling on one CFG pair), x8 prompts per GPU."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config != "t2i":
+        print(json.dumps({"impl": "reference", "unavailable": f"the reference arm times BASELINE configs[1] (t2i) only, not --config {args.config}"}))
+        return
     threads = os.cpu_count() or 1
-    t_probe, _ = cpu_sample_seconds(threads, 1, warm=1)
-    reps = max(1, min(args.steps, int(200.0 / max(t_probe, 1e-3))))
     t0 = time.perf_counter()
-    t_s, ips = cpu_sample_seconds(threads, reps, warm=min(args.warmup, 2))
-    sample = ("1 of 32 LLaDA-8B blocks on one CFG pair (2x1539 token rows, fp32, oracle port of the reference) + "
-              "restricted head + one sampling step on 1024 image rows; images/s extrapolated x32 layers x15 steps")
+    K, W = max(1, args.steps), max(0, args.warmup)
+    t_s, ips = cpu_sample_seconds(threads, K, warm=W)
+    ms_step_extrapolated = 1e3 / ips / STEPS_PER_IMAGE * PROMPTS_PER_GPU       # one denoising step of 8 prompts
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": reps, "warmup": min(args.warmup, 2), "ms_per_step": t_s * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step_extrapolated, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus, C2["n_layers"], 8, PREFIX + 1 + N_IMG + 1, True),
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "sample_repetitions": K, "sample_warmup_repetitions": W, "ms_per_sample": t_s * 1e3,
+            "note": "each timed step = one bounded sample (1/32 of the blocks on 1/8 of the prompts); value and ms_per_step are "
+                    "extrapolated to the whole workload; one host regardless of --gpus",
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
 
@@ -244,11 +389,8 @@ def run_reference(args):
 # ================================================================================================
 # own arm
 # ================================================================================================
-def run_own(args):
+def _dist_setup():
     import torch.distributed as dist
-    from mmada_b200 import MMadaConfig, MMadaModelLM, ops
-    from mmada_b200.prompting import UniPromptingLike, synthetic_t2i_batch
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,6 +410,13 @@ def run_own(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    return dist, world, rank, local, dev
+
+
+def run_own(args):
+    from mmada_b200 import MMadaConfig, MMadaModelLM, ops
+    from mmada_b200.prompting import UniPromptingLike, synthetic_t2i_batch
+    dist, world, rank, local, dev = _dist_setup()
 
     cfgd = dict(C2)
     if args.layers:
@@ -283,12 +432,8 @@ def run_own(args):
     L = cond_h.shape[1]
     from mmada_b200.dist import gather_rows, prompt_seed
     gen = [torch.Generator(device=dev).manual_seed(prompt_seed(1234, rank * B + i)) for i in range(B)]
-    vq = None
-    try:
-        from mmada_b200.modeling_magvitv2 import MAGVITv2
-        vq = MAGVITv2(device=dev).init_random(seed=7)
-    except ImportError:
-        vq = None
+    from mmada_b200.modeling_magvitv2 import MAGVITv2
+    vq = MAGVITv2(device=dev).init_random(seed=7)
 
     def generation(ids_dev, unc_dev, stop=None):
         return model.t2i_generate(input_ids=ids_dev, uncond_input_ids=unc_dev, guidance_scale=GUIDANCE,
@@ -318,31 +463,43 @@ def run_own(args):
     K = args.steps
     full, part = divmod(K, STEPS_PER_IMAGE)
     inputs = [cond_h.to(dev) for _ in range(full + (1 if part else 0))]
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local)              # every rank samples its own GPU (the headline is the max over ranks)
     barrier()
-    if rank == 0:
-        sampler.start()
-    ops.GEMM_EVENTS = [] if not args.no_kernel_events else None
+    sampler.start()
+    if not args.no_kernel_events:
+        ops.GEMM_EVENTS, ops.ATT_EVENTS = [], []
     launches0 = model.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
     for i in range(full):
         generation(inputs[i], unc_d)
     if part:
         generation(inputs[full], unc_d, stop=part)
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3        # the loop has no host sync: time to ENQUEUE K steps
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_own = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_own)
     launches = model.kernel_launches - launches0
-    gemm_events, ops.GEMM_EVENTS = ops.GEMM_EVENTS, None
-    clocks = sampler.stop() if rank == 0 else None
+    gemm_events, att_events = ops.GEMM_EVENTS, ops.ATT_EVENTS
+    ops.GEMM_EVENTS = ops.ATT_EVENTS = None
+    clocks = sampler.stop()
     images = B * world * K / STEPS_PER_IMAGE
     value = images / (ms / 1e3)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, *_ in gemm_events) if gemm_events else None
+    att_ms = sum(a.elapsed_time(b) for a, b, *_ in att_events) if att_events else None
+    mine = {"rank": rank, "ms_per_step": ms_own / K, "gemm_ms_per_step": None if gemm_ms is None else gemm_ms / K,
+            "attention_ms_per_step": None if att_ms is None else att_ms / K, "host_enqueue_ms_per_step": host_enqueue_ms / K,
+            "sm_mhz": clocks.get("sm_mhz"), "power_w_max": clocks.get("power_w_max"), "reasons": clocks.get("reasons")}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
-    # ---- end to end through the public API, host buffers in, host results out
-    G = max(1, K // STEPS_PER_IMAGE)
-    out_h = torch.empty((B, 512, 512, 3) if vq is not None else (B, N_IMG),
-                        dtype=torch.uint8 if vq is not None else torch.int64).pin_memory()
+    # ---- end to end through the public API, host buffers in, host results out: >= 3 whole generations
+    G = max(3, K // STEPS_PER_IMAGE)
+    out_h = torch.empty((B, 512, 512, 3), dtype=torch.uint8).pin_memory()
     barrier()
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_e0.record()
@@ -350,10 +507,7 @@ def run_own(args):
         ids_d = cond_h.to(dev, non_blocking=True)
         un_d = unc_h.to(dev, non_blocking=True)
         codes = generation(ids_d, un_d)
-        if vq is not None:
-            res = vq.decode_code_uint8(codes)
-        else:
-            res = codes
+        res = vq.decode_code_uint8(codes)
         if world > 1:
             res_all = gather_rows(res, B * world)          # the path's only collective (NCCL all-gather)
         out_h.copy_(res, non_blocking=True)
@@ -373,7 +527,7 @@ def run_own(args):
     pk = peaks()
     roof = None
     if gemm_events:
-        tot_ms = sum(a.elapsed_time(b) for a, b, *_ in gemm_events)
+        tot_ms = gemm_ms
         tot_fl = sum(2.0 * M * N * Kk for _, _, M, N, Kk, _ in gemm_events)
         ach = tot_fl / (tot_ms * 1e-3) / 1e12
         by = {}
@@ -381,41 +535,231 @@ def run_own(args):
             k = f"{M}x{N}x{Kk}/epi{ep}"
             t, n, _ = by.get(k, (0.0, 0, 0.0))
             by[k] = (t + a.elapsed_time(b), n + 1, 2.0 * M * N * Kk)
+        traffic, traffic_src = _round_profile("gemm_traffic")
         roof = {"bound": "tensor", "kernel": f"mmada::gemm_kernel<{args.cta_group},*> (tcgen05 UMMA 256x256x16, TMA, TMEM)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "peak_source": pk["source"] + " cuBLAS bf16 sustained", "traffic": _ncu_traffic(),
+                "peak_source": pk["source"] + " cuBLAS bf16 sustained",
+                "traffic": traffic["dram_bytes_per_launch_avg"] if traffic else None,
+                "traffic_source": traffic_src or f"no {ROUND} ncu --set full capture committed yet (earlier rounds' captures are not quoted)",
+                "algorithmic_bytes_per_launch_avg": traffic.get("algorithmic_bytes_per_launch_avg") if traffic else None,
                 "launches": len(gemm_events), "avg_launch_ms": tot_ms / len(gemm_events),
-                "share_of_step": tot_ms / ms,
+                "share_of_step": tot_ms / ms_own,
                 "per_shape": {k: {"ms": t / n, "tflops": fl / (t / n * 1e-3) / 1e12} for k, (t, n, fl) in by.items()}}
+    att = None
+    if att_events:
+        fl = sum(4.0 * Lx * Lx * H * hd * Bx for _, _, Bx, Lx, H, hd in att_events)
+        att = {"kernel": "attention (tcgen05, head_dim 128)", "launches": len(att_events), "ms_per_step": att_ms / K,
+               "avg_launch_ms": att_ms / len(att_events), "tflops": fl / (att_ms * 1e-3) / 1e12,
+               "frac_of_bf16_sustained_peak": fl / (att_ms * 1e-3) / 1e12 / pk["tf_sustained"], "share_of_step": att_ms / ms_own}
     try:
         hbm = hbm_kernel_rooflines(dev, pk["hbm"])
     except Exception as e:          # secondary numbers must not hide the headline
         hbm = {"failed": str(e)}
-    blk, att, head, _ = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
+    lib = None
+    if not args.no_library_baseline:
+        try:
+            lib = library_baseline(dev)
+            lib["speedup_of_this_step"] = lib["ms_per_step"] / (ms / K)
+        except Exception as e:
+            lib = {"failed": str(e)}
+    blk, att_fl, head, _ = algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK)
     caps = masked_caps()
     timed_caps = [caps[i % STEPS_PER_IMAGE] for i in range(K)]             # the K timed steps walk whole generations
     skip = sum(algorithmic_flops_per_step(cfgd, B, L, N_IMG, CODEBOOK, c)[3] for c in timed_caps) / K
-    step_tf = (blk + att + head - skip) / 1e12
+    step_tf = (blk + att_fl + head - skip) / 1e12
     ms_step = ms / K
-    cpu = None
-    if not args.no_cpu_baseline:
+    cpu = cpu_c1 = None
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
         try:
-            t_s, ips = cpu_sample_seconds(os.cpu_count() or 1, 2)
-            cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": "1 of 32 LLaDA-8B blocks on one CFG pair (2x1539 rows, fp32, oracle port) + restricted head + "
-                             "sampling step; extrapolated x32 layers x15 steps"}
+            t_s, ips = cpu_sample_seconds(threads, 2)
+            cpu = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE}
         except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
-            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+            cpu = {"value": None, "unit": "images/s", "cores": threads, "kind": "port", "sample": f"failed: {e}"}
+        try:
+            cpu_c1 = cpu_c1_end_to_end(threads, dev)
+        except Exception as e:
+            cpu_c1 = {"failed": str(e)}
+    parity, parity_src = _round_profile("parity_c2")
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": workload_config(world, cfgd["n_layers"], B, L, vq is not None),
+            "config": workload_config(world, cfgd["n_layers"], B, L, True),
             "tokens_per_sec": value * N_IMG, "algorithmic_tflop_per_step": step_tf,
-            "survey_tflop_per_step": (blk + att + head) / 1e12,
+            "survey_tflop_per_step": (blk + att_fl + head) / 1e12,
             "model_tflops_per_gpu": step_tf / (ms_step * 1e-3), "frac_of_bf16_sustained_peak": step_tf / (ms_step * 1e-3) / pk["tf_sustained"],
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "generations": G},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},
+            "roofline": roof, "attention": att, "hbm_kernels": hbm, "per_rank": per_rank,
+            "cpu_baseline": cpu, "cpu_baseline_c1": cpu_c1, "library_baseline": lib,
+            "parity_c2": None if parity is None else dict(parity, source=parity_src + " (written by tests/test_full_size_gpu.py::"
+                                                          "test_config2_logits_vs_fp32_reference on a B200; not recomputed here)")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ================================================================================================
+# BASELINE configs 3 / 4 / 5 through the same schema
+# ================================================================================================
+def run_other(args):
+    """--config mmu : configs[2] mmu_generate, 512x512 image tokens in context, gen 256, block 32, steps 128, B = 1 per GPU
+       --config text: configs[3] generate(), low-confidence remasking, gen 512, block 64, steps 256, 8 prompts per GPU
+       --config t2m : configs[4] t2m_generate (15 steps, 256 motion tokens) + motion VQ-VAE decode, B = --batch per GPU
+    A "step" is one denoising step (one transformer forward + sampling); the K timed steps are the first K forwards of a
+    generation at the configuration's full sequence length (t2m: a generation of K steps + the decode)."""
+    from mmada_b200 import HumanVQVAE, MMadaConfig, MMadaModelLM, generate, ops
+    from mmada_b200.prompting import UniPromptingLike
+    dist, world, rank, local, dev = _dist_setup()
+    model = MMadaModelLM(MMadaConfig.from_dict(dict(C2)), device=dev).init_random(seed=1234)
+    g = torch.Generator().manual_seed(100 + rank)
+    K, W = max(1, args.steps), max(1, args.warmup)
+    d, f, nl, V = C2["d_model"], C2["mlp_hidden_size"], C2["n_layers"], C2["vocab_size"]
+    pk = peaks()
+    if args.config == "mmu":
+        B, gen_len, blk, name = args.batch or 1, 256, 32, "mmu_new_tokens_per_sec"
+        idx_h = torch.cat([torch.tensor([[126089, 126084]]).expand(B, 2), torch.randint(126349, 126349 + 8192, (B, 1024), generator=g),
+                           torch.full((B, 1), 126085), torch.randint(0, 126000, (B, 64), generator=g)], 1).contiguous().pin_memory()
+        Ltot = idx_h.shape[1] + gen_len
+        steps_per_gen, tok_per_step = 128, gen_len / 128.0
+        workload = f"MMaDA-8B-arch mmu_generate: 1024 image tokens + 64-token question in context, gen 256, block 32, 128 steps, B={B}/GPU"
+
+        def run(n_steps, ids):          # the first n_steps forwards of one generation (sequence length unchanged)
+            return model.mmu_generate(ids, max_new_tokens=gen_len, steps=128, block_length=blk, stop_after_steps=n_steps)
+        rows_sampled, sample_cols = B * blk, V
+    elif args.config == "text":
+        B, gen_len, blk, name = args.batch or 8, 512, 64, "text_new_tokens_per_sec"
+        idx_h = torch.randint(0, 126000, (B, 64), generator=g).pin_memory()
+        Ltot = 64 + gen_len
+        steps_per_gen, tok_per_step = 256, gen_len / 256.0
+        workload = f"MMaDA-8B-arch generate(): low-confidence remasking, prompt 64, gen 512, block 64, 256 steps, T=0, B={B}/GPU"
+
+        def run(n_steps, ids):
+            return generate(model, ids, steps=256, gen_length=gen_len, block_length=blk, temperature=0.0, cfg_scale=0.0,
+                            remasking="low_confidence", stop_after_steps=n_steps)
+        rows_sampled, sample_cols = B * blk, V
+    else:
+        B, name = args.batch or 1, "t2m_motions_per_sec"
+        P, N = 257, 256
+        idx_h = torch.cat([torch.randint(0, 126000, (B, P), generator=g), torch.full((B, 1), 126084),
+                           torch.full((B, N), 126336), torch.full((B, 1), 126085)], 1).pin_memory()
+        Ltot = idx_h.shape[1]
+        steps_per_gen, tok_per_step = 15, N / 15.0
+        up = UniPromptingLike()
+        vqm = HumanVQVAE(device=dev).init_random(seed=3)
+        workload = f"MMaDA-8B-arch t2m_generate: 256 motion tokens, 15 steps, L=515, + motion VQ-VAE decode, B={B}/GPU"
+
+        def run(n_steps, ids):
+            # the 134656-entry vocabulary of the random-init model has no room behind the image codes: motion codes
+            # are read from the image-code slice (image_codebook_size=0); same arithmetic
+            toks = model.t2m_generate(input_ids=ids, timesteps=n_steps, seq_len=N, uni_prompting=up, temperature=1.0,
+                                      image_codebook_size=0)
+            return vqm.forward_decoder_batched(toks.clamp(0, 511))
+        rows_sampled, sample_cols = B * N, 512
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # a whole generation of the semi-autoregressive configs takes 128 / 256 forwards: the K timed steps are the first K
+    K = min(K, steps_per_gen) if args.config != "t2m" else K
+    run(W, idx_h.to(dev).clone())
+    Kr = K
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ops.GEMM_EVENTS = []
+    l0 = model.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ids_d = idx_h.to(dev).clone()
+    t_h0 = time.perf_counter()
+    e0.record()
+    run(K, ids_d)
+    e1.record()
+    host_ms = (time.perf_counter() - t_h0) * 1e3
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    gemm_events, ops.GEMM_EVENTS = ops.GEMM_EVENTS, None
+    launches = model.kernel_launches - l0
+    clocks = sampler.stop()
+    # e2e: host prompt in, host result out, one whole generation of K-equivalent steps
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    res = run(K, idx_h.to(dev, non_blocking=True).clone())
+    res_h = res.cpu()
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    units_per_step = B * world * (tok_per_step if args.config != "t2m" else 1.0 / steps_per_gen)
+    value = units_per_step * Kr / (ms / 1e3)
+    roof = None
+    if gemm_events:
+        tot_ms = sum(a.elapsed_time(b) for a, b, *_ in gemm_events)
+        tot_fl = sum(2.0 * M * N * Kk for _, _, M, N, Kk, _ in gemm_events)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        # a forward on M = B*L rows must also stream the 14 GB of block weights once: the bound is the larger of the two
+        w_bytes = 2.0 * nl * (4 * d * d + 3 * d * f)
+        t_tensor = tot_fl / len(gemm_events) / (pk["tf_sustained"] * 1e12)
+        roof = {"bound": "tensor", "kernel": "mmada::gemm_kernel (forward GEMMs)", "achieved": ach, "peak": pk["tf_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None, "launches": len(gemm_events),
+                "avg_launch_ms": tot_ms / len(gemm_events), "share_of_step": tot_ms / ms,
+                "weights_stream_floor_ms_per_step": w_bytes / (pk["hbm"] * 1e9) * 1e3,
+                "tensor_floor_ms_per_step": t_tensor * len(gemm_events) / Kr * 1e3}
+    # the sampling kernel of the path, timed alone: B*block rows x V fp32 logits read once
+    hbm = None
+    try:
+        R = rows_sampled
+        lg = torch.randn(R, sample_cols, device=dev)
+        if args.config == "t2m":
+            q = torch.empty(R, sample_cols, device=dev).exponential_(1)
+            u = torch.rand(B, 256, device=dev)
+            known = torch.full((B, 256), 126336, dtype=torch.int64, device=dev)
+            tickets = torch.zeros(B, dtype=torch.int32, device=dev)
+            fn = lambda: ops.t2i_sample_step(lg, None, q, u, known.clone(), None, 0, tickets, 0.0, 100.0, 0.5, 126336, 126349)
+            nbytes, kname = 2 * R * sample_cols * 4, "t2i_sample_kernel (motion slice)"
+        else:
+            fn = lambda: ops.text_sample_rows(lg, None, 0.0, 0.0)
+            nbytes, kname = R * sample_cols * 4, "text_sample_kernel (T=0: argmax + fp64 softmax confidence)"
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b) / 10
+        hbm = {kname: {"ms": t, "algorithmic_bytes": nbytes, "achieved": nbytes / t / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                       "frac": nbytes / t / 1e6 / pk["hbm"],
+                       "note": "operand smaller than the 126 MB L2 when R*V*4 < 126e6: then an L2-resident number, not HBM"}}
+    except Exception as e:
+        hbm = {"failed": str(e)}
+    line = {"metric": name, "value": value, "unit": "motions/s" if args.config == "t2m" else "tokens/s", "n_gpus": world,
+            "steps": K, "steps_run": Kr, "warmup": W, "ms_per_step": ms / Kr, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "n_layers": nl, "batch_per_gpu": B, "seq_len": Ltot,
+                       "parallelism": f"prompt-shard x{world}", "l2": "inputs_exceed_l2 (16 GB of weights streamed per step)"},
+            "e2e": {"value": units_per_step * Kr / (ms_e2e / 1e3), "unit": "motions/s" if args.config == "t2m" else "tokens/s",
+                    "h2d_bytes_per_step": idx_h.numel() * 8 / Kr, "d2h_bytes_per_step": res_h.numel() * res_h.element_size() / Kr},
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms / Kr,
+            "launch_bound": bool(host_ms > 0.9 * ms),
+            "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},
+            "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": None}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -427,15 +771,20 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=15)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", default="t2i", choices=["t2i", "mmu", "text", "t2m"])
+    ap.add_argument("--batch", type=int, default=0, help="--config mmu/text/t2m: prompts per GPU (default 1 / 8 / 1)")
     ap.add_argument("--cta-group", type=int, default=2)
     ap.add_argument("--layers", type=int, default=0, help="debug: override layer count (result is then not the benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-kernel-events", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.config == "t2i":
         run_own(args)
+    else:
+        run_other(args)
 
 
 if __name__ == "__main__":

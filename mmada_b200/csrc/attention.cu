@@ -382,11 +382,8 @@ static int launch_attention(const void* q, const void* k, const void* v, int64_t
     if ((st = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box))) return st;
     if ((st = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box))) return st;
     auto kern = attention_kernel<HD, POLY>;
-    static bool configured = false;
-    if (!configured) {
-        MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    MMADA_CUDA_TRY(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, configured));
     AttnParams p;
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
@@ -401,13 +398,12 @@ static int launch_attention(const void* q, const void* k, const void* v, int64_t
     return cuda_status(cudaGetLastError());
 }
 
-// share of the exponentials on the FMA pipe, in eighths (tuning knob MMADA_ATT_POLY; -1 = not set: every kernel
+// share of the exponentials on the FMA pipe, in eighths (EXPERIMENTS builds: MMADA_ATT_POLY; -1 = not set: every kernel
 // then uses the default its own measurements gave)
 static int attention_poly_env() {
     static int v = -2;
     if (v == -2) {
-        const char* e = getenv("MMADA_ATT_POLY");
-        v = e ? atoi(e) : -1;
+        v = experiment_env("MMADA_ATT_POLY", -1);
         if (v != 0 && v != 2 && v != 3 && v != 4) v = -1;
     }
     return v;
@@ -428,9 +424,6 @@ static int dispatch_attention(const void* q, const void* k, const void* v, int64
 // attention_pair.cu: persistent CTA pairs, head_dim 128
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream);
-// attention_split.cu: persistent CTA pairs, key tiles split between two softmax agents, head_dim 128, L > 128
-int launch_attention_split(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
-                           int Lq, int H, float scale, cudaStream_t stream);
 
 }  // namespace mmada
 
@@ -449,31 +442,15 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
         return kBadArgument;
     cudaStream_t s = (cudaStream_t)stream;
     if (head_dim == 128) {
-        static int use_pair = -1;       // MMADA_ATT_PAIR=0 selects the single-CTA kernel (kept for head_dim 64 and A/B runs)
-        if (use_pair < 0) {
-            const char* e = getenv("MMADA_ATT_PAIR");
-            use_pair = e ? atoi(e) != 0 : 1;
-        }
+        static const int use_pair = experiment_env("MMADA_ATT_PAIR", 1);        // 0: single-CTA kernel (A/B runs)
         if (use_pair && L > 128) {
             // A pair item is 256 query rows.  When the last item of every (batch, head) would hold at most one
             // 128-row tile (L = 1539: 3 rows), those rows go to the single-CTA kernel instead (one CTA per
             // (batch, head), a second launch on the same stream) and the pair kernel walks whole items only:
             // worth it once the extra items would cost the pairs a wave of their own.
-            static int split_tail = -1;     // MMADA_ATT_SPLIT_TAIL=0 disables
-            if (split_tail < 0) {
-                const char* e = getenv("MMADA_ATT_SPLIT_TAIL");
-                split_tail = e ? atoi(e) != 0 : 1;
-            }
-            // MMADA_ATT_SPLIT=1 selects attention_split.cu (key tiles split between two softmax agents with their own
-            // accumulators: measured 0.74 ms against 0.69 ms at config 2) instead of attention_pair.cu
-            static int use_split = -1;
-            if (use_split < 0) {
-                const char* e = getenv("MMADA_ATT_SPLIT");
-                use_split = e ? atoi(e) != 0 : 0;
-            }
+            static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
             auto pair = [&](int Lq) {
-                return use_split ? launch_attention_split(q, k, v, ld, out, ldo, B, L, Lq, H, scale, s)
-                                 : launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
+                return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
             };
             const int rem = L % 256;
             if (split_tail && L > 256 && rem > 0 && rem <= 128 && B * H >= num_sms()) {

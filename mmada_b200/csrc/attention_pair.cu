@@ -510,11 +510,8 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
     if ((st = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, k, dims, strides, box64))) return st;
     if ((st = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, v, dims, strides, box128))) return st;
     auto kern = attention_pair_kernel<POLY, MAXCHK>;
-    static bool configured = false;
-    if (!configured) {
-        MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    MMADA_CUDA_TRY(ensure_dynamic_smem(kern, P_SMEM_BYTES, configured));
     PairParams p = {};
     p.out = (__nv_bfloat16*)out;
     p.ldo = ldo;
@@ -549,11 +546,8 @@ int launch_pair(const void* q, const void* k, const void* v, int64_t ld, void* o
 // FMA pipe), < 0 when not set
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream) {
-    static int maxchk = -1;             // MMADA_ATT_MAXCHK=1: take the row maxima of every tile (the previous scheme; A/B runs)
-    if (maxchk < 0) {
-        const char* e = getenv("MMADA_ATT_MAXCHK");
-        maxchk = e ? atoi(e) != 0 : 0;
-    }
+    // EXPERIMENTS builds, MMADA_ATT_MAXCHK=1: take the row maxima of every tile (the previous scheme; A/B runs)
+    static const int maxchk = experiment_env("MMADA_ATT_MAXCHK", 0);
     if (maxchk) {
         switch (poly) {
             case 0: return launch_pair<0, true>(q, k, v, ld, out, ldo, B, L, Lq, H, scale, stream);

@@ -26,9 +26,12 @@ __global__ void __launch_bounds__(256) embed_kernel(const int64_t* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * chunks;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int m = (int)(i / chunks), c = (int)(i % chunks);
-        int64_t id = ids[m];
-        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(table + id * d) + c);
+        // an id outside the table (nn.Embedding raises a device assert there, reference modeling_llada.py:1222) yields a
+        // row of NaNs: every logit of the sequence turns NaN instead of the bad id being clamped to a valid row
+        const int64_t id = ids[m];
+        const bool ok = id >= 0 && id < vocab;
+        const uint4 w = ok ? __ldg(reinterpret_cast<const uint4*>(table + id * d) + c)
+                           : make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
         float4 a, b;
         float2 t;
@@ -61,14 +64,14 @@ __global__ void __launch_bounds__(256) embed_norm_kernel(const int64_t* __restri
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (m >= M) return;
-    int64_t id = ids[m];
-    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-    const uint4* src = reinterpret_cast<const uint4*>(table + id * d);
+    const int64_t id = ids[m];
+    const bool ok = id >= 0 && id < vocab;                     // out of range: a row of NaNs (see embed_kernel)
+    const uint4* src = reinterpret_cast<const uint4*>(table + (ok ? id : 0) * d);
     uint4* xbr = reinterpret_cast<uint4*>(xb + (int64_t)m * d);
     float4* o = reinterpret_cast<float4*>(out + (int64_t)m * d);
     float ss = 0.f;
     for (int c = lane; c < (d >> 3); c += 32) {
-        const uint4 w = __ldg(src + c);
+        const uint4 w = ok ? __ldg(src + c) : make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
         float4 a, b;
         float2 t;

@@ -557,11 +557,8 @@ template <int CG, int EPI, int BN, bool CONV>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<CG, BN>;
     auto kern = gemm_kernel<CG, EPI, BN, CONV>;
-    static bool configured = false;
-    if (!configured) {
-        MMADA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    MMADA_CUDA_TRY(ensure_dynamic_smem(kern, Cfg::SMEM_BYTES, configured));
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     int clusters = num_sms() / CG;
     if (clusters > num_tiles) clusters = num_tiles;
@@ -622,22 +619,28 @@ static int dispatch_conv256(int epi, const CUtensorMap& ma, const CUtensorMap& m
 
 using namespace mmada;
 
-// rasterisation / cache-hint defaults, overridable for experiments (MMADA_GEMM_GROUP_M, MMADA_GEMM_HINTS=ab with
-// a,b in {n,f,l} = normal / evict-first / evict-last for the A and B operand loads)
+// rasterisation / cache hints.  Defaults measured in round 1 (profiles/r01b_gemm_traffic_probe.txt); an EXPERIMENTS=1
+// build can override them from the environment (MMADA_GEMM_GROUP_M, MMADA_GEMM_HINTS=ab with a,b in {n,f,l} = normal /
+// evict-first / evict-last for the A and B operand loads) — the product library reads no environment variables.
 static void set_tuning(GemmParams& p) {
-    static int group_m = -1;
-    static uint64_t ha = kEvictLast, hb = kEvictNormal;   // measured: +2 % sustained vs (8, normal/normal)
-    if (group_m < 0) {
+    int group_m = 0;
+    uint64_t ha = kEvictLast, hb = kEvictNormal;          // measured: +2 % sustained vs (8, normal/normal)
+#ifdef MMADA_EXPERIMENTS
+    static int env_group_m = -1;
+    static uint64_t env_ha = kEvictLast, env_hb = kEvictNormal;
+    if (env_group_m < 0) {
         const char* g = getenv("MMADA_GEMM_GROUP_M");
-        group_m = g ? atoi(g) : 0;
-        if (group_m < 0) group_m = 0;
+        env_group_m = g ? atoi(g) : 0;
+        if (env_group_m < 0) env_group_m = 0;
         const char* h = getenv("MMADA_GEMM_HINTS");
         auto dec = [](char c) { return c == 'f' ? kEvictFirst : (c == 'l' ? kEvictLast : kEvictNormal); };
-        if (h && h[0] && h[1]) { ha = dec(h[0]); hb = dec(h[1]); }
+        if (h && h[0] && h[1]) { env_ha = dec(h[0]); env_hb = dec(h[1]); }
     }
+    group_m = env_group_m; ha = env_ha; hb = env_hb;
+#endif
     // default: 16 m-tiles per group (the A band, 16 x 256 rows x K, stays in L2 while the n-tiles sweep past it);
-    // for long K the band outgrows L2 and a squarer wave re-reads less (profiles/r01b_gemm_traffic_probe.txt:
-    // K = 12288: 3.7 GB at 8 against 4.1 GB at 16; K = 4096: 2.5 GB at 16 against 3.5 GB at 8)
+    // for long K the band outgrows L2 and a squarer wave re-reads less (K = 12288: 3.7 GB at 8 against 4.1 GB at 16;
+    // K = 4096: 2.5 GB at 16 against 3.5 GB at 8)
     p.group_m = group_m ? group_m : (p.K >= 8192 ? 8 : 16);
     p.hint_a = ha; p.hint_b = hb;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace mmada {
 
@@ -24,14 +25,42 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? kOk : 1000 + (
         if (_e != cudaSuccess) return cuda_status(_e); \
     } while (0)
 
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several)
 inline int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return cached;
+    static int cached[kMaxDevices] = {};
+    const int dev = current_device();
+    if (cached[dev] == 0) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: `done` is the launcher's per-kernel flag array
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes, bool (&done)[kMaxDevices]) {
+    const int dev = current_device();
+    if (done[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
+// Tuning switches read from the environment exist only in EXPERIMENTS=1 builds (csrc/Makefile); the product library
+// always takes the default.
+inline int experiment_env(const char* name, int dflt) {
+#ifdef MMADA_EXPERIMENTS
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

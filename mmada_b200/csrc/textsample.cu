@@ -121,7 +121,9 @@ text_sample_kernel(const float* __restrict__ logits, const float* __restrict__ u
         if (lane == 0) { s_bi = best.i; s_bcast[0] = (double)mx; }
     }
     __syncthreads();
-    const int x0 = s_bi;
+    // a row with no comparable value (every logit NaN) leaves the sentinel: commit token 0 with a NaN confidence, like
+    // torch.argmax over an all-NaN row, instead of indexing the row with 0x7fffffff
+    const int x0 = s_bi == 0x7fffffff ? 0 : s_bi;
     const double m = s_bcast[0];
     // ---- pass 2: fp64 softmax denominator (the row is L2-resident from pass 1)
     double sum = 0.0;

@@ -38,17 +38,25 @@ def _model_device(model):
 def generate(model, prompt, steps=128, gen_length=128, block_length=128, temperature=0.,
              cfg_scale=0., remasking='low_confidence', mask_id=126336, attention_mask=None, *,
              noise: Optional[Sequence[torch.Tensor]] = None, eot_token: Optional[int] = None, seed: Optional[int] = None,
-             trace: Optional[list] = None):
+             trace: Optional[list] = None, stop_after_steps: Optional[int] = None):
     """Same positional/keyword arguments as the reference.  ``model`` must be an
     ``mmada_b200.LLaDAModelLM`` (it provides ``logits_rows``).  ``attention_mask`` is accepted and has
-    no effect, as in the reference (the bias built from it is never applied, Q1).  Keyword-only
+    no effect, as in the reference (the bias built from it is never applied, Q1).  Precondition: ``prompt`` holds no
+    ``mask_id`` (raises otherwise; the reference would also unmask masked prompt positions).  Keyword-only
     extras: ``noise`` (per forward k, fp64 uniforms (B, block_length, V) for the block's rows),
-    ``eot_token`` (mmu_generate_fast's early exit), ``seed`` for the in-kernel generator."""
+    ``eot_token`` (mmu_generate_fast's early exit), ``seed`` for the in-kernel generator, ``stop_after_steps``
+    (benchmarking hook: return after that many forwards, sequence length unchanged)."""
     if remasking not in ('low_confidence', 'random'):
         raise NotImplementedError(remasking)
     dev = _model_device(model)
     prompt = prompt.to(dev)
     B, Lp = prompt.shape
+    # Precondition of the block restriction (module docstring, Q21): the prompt holds no mask_id.  The reference ranks
+    # every still-masked position before the block end (generate.py:98-111), so a masked PROMPT position would be a
+    # transfer candidate there and never here — refuse instead of diverging silently (one host read per call).
+    if bool((prompt == mask_id).any()):
+        raise NotImplementedError("generate(): the prompt contains mask_id tokens (infilling-style input); this "
+                                  "implementation only ranks the still-masked positions of the current block")
     L = Lp + gen_length
     x = torch.full((B, L), mask_id, dtype=torch.long, device=dev)
     x[:, :Lp] = prompt.clone()
@@ -69,6 +77,8 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
         cnt = ops.block_mask_count(x, lo, block_length, mask_id)
         rows = (rows_base + lo).reshape(-1).contiguous()
         for i in range(steps):
+            if stop_after_steps is not None and k >= stop_after_steps:
+                return x
             if cfg:
                 un_x = x.clone()
                 un_x[prompt_index] = mask_id

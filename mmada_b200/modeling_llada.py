@@ -30,6 +30,18 @@ from . import ops
 _P = "model.transformer."
 
 
+#: reference ModelConfig options (models/configuration_llada.py:129-363) that change the arithmetic of the forward and
+#: that these kernels do not implement: a config / checkpoint that sets one of them to anything but the value MMaDA-8B
+#: uses is REJECTED instead of loading and silently producing other logits.  key -> accepted values
+_SUPPORTED = {
+    "block_type": ("llama",), "activation_type": ("silu",), "layer_norm_type": ("rms",), "rope": (True,), "alibi": (False,),
+    "include_bias": (False,), "include_qkv_bias": (False, None), "bias_for_layer_norm": (False, None),
+    "weight_tying": (False,), "scale_logits": (False,), "input_emb_norm": (False,), "attention_layer_norm": (False,),
+    "multi_query_attention": (False, None), "layer_norm_with_affine": (True,), "rope_full_precision": (True,),
+    "clip_qkv": (None,), "embedding_dropout": (0, 0.0), "residual_dropout": (0, 0.0), "attention_dropout": (0, 0.0),
+}
+
+
 @dataclass
 class LLaDAConfig:
     """The subset of the reference's ModelConfig (models/configuration_llada.py:129-384) the path uses."""
@@ -42,14 +54,37 @@ class LLaDAConfig:
     rms_norm_eps: float = 1e-5
     max_sequence_length: int = 4096
     mask_token_id: int = 126336
+    embedding_size: Optional[int] = None      # rows of wte / ff_out when it differs from vocab_size (reference :309)
 
     @classmethod
     def from_dict(cls, d: dict) -> "LLaDAConfig":
+        """Accepts the reference's full ModelConfig / HF ``config.json`` dict.  Options that would change the math
+        (GQA, biases, tied head, scaled logits, q/k norms, other block / norm / activation types, ALiBi) raise."""
+        d = dict(d)
+        bad = []
+        for k, ok in _SUPPORTED.items():
+            if k in d:
+                v = d[k]
+                v = getattr(v, "value", v)                  # the reference's StrEnum members
+                v = str(v) if isinstance(v, str) else v
+                if v not in ok:
+                    bad.append(f"{k}={d[k]!r} (supported: {', '.join(map(repr, ok))})")
+        nh = d.get("n_heads", cls.n_heads)
+        if d.get("n_kv_heads") not in (None, nh):
+            bad.append(f"n_kv_heads={d['n_kv_heads']!r} != n_heads={nh} (grouped-query attention is not implemented)")
+        if d.get("mlp_hidden_size") is None and "mlp_ratio" in d and "d_model" in d:
+            d["mlp_hidden_size"] = int(d["mlp_ratio"]) * int(d["d_model"])
+        if bad:
+            raise ValueError("mmada_b200 implements the MMaDA-8B configuration of LLaDA only; unsupported: " + "; ".join(bad))
         return cls(**{k: d[k] for k in cls.__dataclass_fields__ if k in d})
 
     @property
     def head_dim(self) -> int:
         return self.d_model // self.n_heads
+
+    @property
+    def vocab_rows(self) -> int:
+        return self.embedding_size or self.vocab_size
 
 
 def interleave_gate_up(w_gate: torch.Tensor, w_up: torch.Tensor, block: int = 128) -> torch.Tensor:
@@ -101,30 +136,72 @@ class LLaDAModelLM:
         self.kernel_launches = 0          # launches of this package's kernels (bench.py reports it)
 
     # ---- weights ---------------------------------------------------------------------------
+    def _w(self, sd, k, norm=None):
+        t = sd[k].to(device=self.device)
+        if norm is not None and self.fused_norm:        # fold the preceding RMSNorm's weight into the columns
+            t = t.float() * sd[norm].to(device=self.device, dtype=torch.float32)[None, :]
+        return t.to(dtype=torch.bfloat16).contiguous()
+
+    def _n(self, sd, k):
+        return sd[k].to(device=self.device, dtype=torch.float32).contiguous()
+
+    def load_block(self, sd, i: int) -> None:
+        """Layer ``i`` from a mapping that holds (at least) that block's tensors under the reference's key names.
+        Lets a caller stream a checkpoint shard by shard / layer by layer instead of holding it whole."""
+        c = self.config
+        b = f"{_P}blocks.{i}."
+        an, fn = b + "attn_norm.weight", b + "ff_norm.weight"
+        d, f = c.d_model, c.mlp_hidden_size
+        for k, shp in ((b + "q_proj.weight", (d, d)), (b + "k_proj.weight", (d, d)), (b + "v_proj.weight", (d, d)),
+                       (b + "attn_out.weight", (d, d)), (b + "ff_proj.weight", (f, d)), (b + "up_proj.weight", (f, d)),
+                       (b + "ff_out.weight", (d, f)), (an, (d,)), (fn, (d,))):
+            if tuple(sd[k].shape) != shp:
+                # e.g. a grouped-query checkpoint (k_proj / v_proj with fewer rows): refuse rather than mis-concatenate
+                raise ValueError(f"{k}: shape {tuple(sd[k].shape)} does not match the configuration's {shp}")
+        wqkv = torch.cat([self._w(sd, b + "q_proj.weight", an), self._w(sd, b + "k_proj.weight", an),
+                          self._w(sd, b + "v_proj.weight", an)], 0).contiguous()
+        layer = _Layer(self._n(sd, an), wqkv, self._w(sd, b + "attn_out.weight"), self._n(sd, fn),
+                       interleave_gate_up(self._w(sd, b + "ff_proj.weight", fn), self._w(sd, b + "up_proj.weight", fn)),
+                       self._w(sd, b + "ff_out.weight"))
+        while len(self.layers) <= i:
+            self.layers.append(None)
+        self.layers[i] = layer
+
+    def load_embeddings(self, sd) -> None:
+        """wte, ln_f and the output head; their row count is taken from the tensors (embedding_size may exceed
+        vocab_size, reference modeling_llada.py:1062,1088)."""
+        self.wte = self._w(sd, _P + "wte.weight")
+        self.ln_f = self._n(sd, _P + "ln_f.weight")
+        self.head = self._w(sd, _P + "ff_out.weight")
+        d = self.config.d_model
+        if self.wte.shape[1] != d or self.head.shape[1] != d or self.ln_f.numel() != d:
+            raise ValueError("wte / ln_f / ff_out do not match d_model")
+        if self.head.shape[0] != self.wte.shape[0]:
+            raise ValueError(f"wte has {self.wte.shape[0]} rows, ff_out {self.head.shape[0]}")
+
+    @staticmethod
+    def check_state_dict_keys(keys) -> None:
+        """Raise on tensors this implementation would otherwise ignore and so compute something else than the
+        reference does with them: biases (include_bias / include_qkv_bias), q_norm / k_norm (attention_layer_norm),
+        fused att_proj / ff_proj layouts of the non-llama block types."""
+        bad = [k for k in keys
+               if k.endswith(".bias") or ".q_norm." in k or ".k_norm." in k or ".att_proj." in k or ".attn_norm.bias" in k
+               or k.endswith("wpe.weight") or ".emb_norm." in k]
+        if bad:
+            raise ValueError(f"state dict holds tensors of unsupported LLaDA options: {bad[:6]}{' ...' if len(bad) > 6 else ''}")
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> "LLaDAModelLM":
-        """``sd`` uses the reference's key names."""
-        c, dev = self.config, self.device
-
-        def w(k, norm=None):
-            t = sd[k].to(device=dev)
-            if norm is not None and self.fused_norm:        # fold the preceding RMSNorm's weight into the columns
-                t = t.float() * sd[norm].to(device=dev, dtype=torch.float32)[None, :]
-            return t.to(dtype=torch.bfloat16).contiguous()
-
-        def n(k):
-            return sd[k].to(device=dev, dtype=torch.float32).contiguous()
-
-        self.wte = w(_P + "wte.weight")
+        """``sd`` uses the reference's key names.  Any Mapping works, including lazy ones that
+        materialise a tensor on access (tests/test_full_size_gpu.py streams an 8B model through one)."""
+        if hasattr(sd, "keys"):
+            try:
+                self.check_state_dict_keys(list(sd.keys()))
+            except TypeError:
+                pass
         self.layers = []
-        for i in range(c.n_layers):
-            b = f"{_P}blocks.{i}."
-            an, fn = b + "attn_norm.weight", b + "ff_norm.weight"
-            wqkv = torch.cat([w(b + "q_proj.weight", an), w(b + "k_proj.weight", an), w(b + "v_proj.weight", an)], 0).contiguous()
-            self.layers.append(_Layer(n(an), wqkv, w(b + "attn_out.weight"), n(fn),
-                                      interleave_gate_up(w(b + "ff_proj.weight", fn), w(b + "up_proj.weight", fn)),
-                                      w(b + "ff_out.weight")))
-        self.ln_f = n(_P + "ln_f.weight")
-        self.head = w(_P + "ff_out.weight")
+        self.load_embeddings(sd)
+        for i in range(self.config.n_layers):
+            self.load_block(sd, i)
         return self
 
     def init_random(self, seed: int = 0, std_scale: float = 1.0) -> "LLaDAModelLM":
@@ -139,14 +216,14 @@ class LLaDAModelLM:
             t.normal_(0.0, std * std_scale, generator=g)
             return t
 
-        self.wte = rnd((c.vocab_size, d), d ** -0.5)
+        self.wte = rnd((c.vocab_rows, d), d ** -0.5)
         self.layers = []
         for i in range(c.n_layers):
             r = (2 * (i + 1)) ** -0.5
             self.layers.append(_Layer(torch.ones(d, device=dev), rnd((3 * d, d), d ** -0.5), rnd((d, d), r * d ** -0.5),
                                       torch.ones(d, device=dev), rnd((2 * f, d), d ** -0.5), rnd((d, f), r * f ** -0.5)))
         self.ln_f = torch.ones(d, device=dev)
-        self.head = rnd((c.vocab_size, d), d ** -0.5)
+        self.head = rnd((c.vocab_rows, d), d ** -0.5)
         return self
 
     def _rope_tables(self, seq_len: int):
@@ -239,7 +316,7 @@ class LLaDAModelLM:
         early = rows is not None and self.restrict_last_block and 10 * rows.numel() <= 9 * input_ids.numel()
         x = self.hidden_states(input_ids, rows if early else None)
         xn = ops.rmsnorm(x, self.ln_f, c.rms_norm_eps, rows=None if early else rows)
-        col_hi = c.vocab_size if col_hi is None else col_hi
+        col_hi = self.head.shape[0] if col_hi is None else col_hi
         self.kernel_launches += 2
         return ops.gemm(xn, self.head[col_lo:col_hi], ops.EPI_F32, cta_group=self.cta_group)
 

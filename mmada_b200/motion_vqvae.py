@@ -54,6 +54,31 @@ class HumanVQVAE:
         self._conv(sd, f"{D}{4 + self.down_t}", "out")
         return self
 
+    def init_random(self, seed: int = 0) -> "HumanVQVAE":
+        """Random decoder weights with the reference's shapes, drawn on the device (benchmarks: no checkpoint offline)."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        W, cd = self.width, self.code_dim
+
+        def rnd(shape, std):
+            return torch.randn(shape, generator=g, device=self.device, dtype=torch.float32) * std
+
+        sd = {"quantizer.codebook": rnd((self.nb_code, cd), 1.0)}
+        D = "decoder.model."
+
+        def conv(name, co, ci, k):
+            sd[f"{D}{name}.weight"] = rnd((co, ci, k), (ci * k) ** -0.5)
+            sd[f"{D}{name}.bias"] = rnd((co,), 0.02)
+
+        conv("0", W, cd, 3)
+        for i in range(self.down_t):
+            for j in range(self.depth):
+                conv(f"{2 + i}.0.model.{j}.conv1", W, W, 3)
+                conv(f"{2 + i}.0.model.{j}.conv2", W, W, 1)
+            conv(f"{2 + i}.2", W, W, 3)
+        conv(f"{2 + self.down_t}", W, W, 3)
+        conv(f"{4 + self.down_t}", self.n_feats, W, 3)
+        return self.load_state_dict(sd)
+
     # ---- decoder -----------------------------------------------------------------------------
     def _c(self, x, key, taps, dilation=1, upsample=1, relu=False, resid=None):
         """Conv1d(k = taps, dilation, 'same' padding) of act(x), x fp32 [B,T,C] -> fp32 [B, T*upsample, Cout]."""

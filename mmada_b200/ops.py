@@ -15,10 +15,29 @@ EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_BF16, EPI_BIAS_BF16, EPI_BIAS_F32, 
 #: when set to a list, every GEMM launch appends (start_event, end_event, M, N, K, epilogue) — used by
 #: bench.py to time the dominant kernel live on the launching stream
 GEMM_EVENTS = None
+#: the same for the attention launches: (start_event, end_event, batch, seq_len, n_heads, head_dim)
+ATT_EVENTS = None
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _call(tensors, name: str, *args) -> None:
+    """Launch ``name`` on the current stream of the operands' device (all operands must share one CUDA device; the
+    current device is switched for the call when it is another one)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.MMadaKernelError(f"{name}: CPU tensor passed (mmada_b200 has no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.MMadaKernelError(f"{name}: operands on different devices ({dev} and {t.device})")
+    idx = dev.index
+    if idx == torch.cuda.current_device():
+        _lib.call(name, *args, torch.cuda.current_stream(idx).cuda_stream)
+    else:
+        with torch.cuda.device(idx):
+            _lib.call(name, *args, torch.cuda.current_stream(idx).cuda_stream)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -53,8 +72,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, out: Option
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.call("mmada_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
-              _ptr(aux), _ptr(bias), M, N, K, epilogue, cta_group, _stream())
+    _call((a, w, out, aux, bias,), "mmada_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+              _ptr(aux), _ptr(bias), M, N, K, epilogue, cta_group)
     if ev is not None:
         e1.record()
         ev.append((e0, e1, M, N, K, epilogue))
@@ -75,8 +94,8 @@ def gemm_qkv_rope(a: torch.Tensor, wqkv: torch.Tensor, sin: torch.Tensor, cos: t
     if ev is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.call("mmada_gemm_qkv_rope_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0), out.data_ptr(),
-              out.stride(0), sin.data_ptr(), cos.data_ptr(), M, N, K, 2 * d_model, head_dim, seq_len, cta_group, _stream())
+    _call((a, wqkv, out, sin, cos,), "mmada_gemm_qkv_rope_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0), out.data_ptr(),
+              out.stride(0), sin.data_ptr(), cos.data_ptr(), M, N, K, 2 * d_model, head_dim, seq_len, cta_group)
     if ev is not None:
         e1.record()
         ev.append((e0, e1, M, N, K, 7))
@@ -110,8 +129,8 @@ def gemm_resid_norm(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, xb: torch
     assert a.stride(1) == 1 and w.stride(1) == 1 and x.shape == (M, N) and xb.shape == (M, N)
     assert x.stride(1) == 1 and xb.stride(1) == 1 and N % 256 == 0 and ssq.is_contiguous() and ssq.numel() >= M * (N // 256)
     e0, rest = _timed(M, N, K, EPI_RESID_F32)
-    _lib.call("mmada_gemm_resid_norm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), x.stride(0),
-              xb.data_ptr(), xb.stride(0), ssq.data_ptr(), M, N, K, cta_group, _stream())
+    _call((a, w, x, xb, ssq,), "mmada_gemm_resid_norm_f32", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), x.data_ptr(), x.stride(0),
+              xb.data_ptr(), xb.stride(0), ssq.data_ptr(), M, N, K, cta_group)
     _timed_end(e0, rest)
     return x
 
@@ -127,8 +146,8 @@ def gemm_swiglu_rownorm(a: torch.Tensor, w: torch.Tensor, ssq: torch.Tensor, ssq
         out = torch.empty((M, N // 2), dtype=torch.bfloat16, device=a.device)
     assert out.shape == (M, N // 2) and out.stride(1) == 1
     e0, rest = _timed(M, N, K, EPI_SWIGLU_BF16)
-    _lib.call("mmada_gemm_swiglu_rownorm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
-              out.stride(0), ssq.data_ptr(), ssq_tiles, norm_dim, float(eps), M, N, K, cta_group, _stream())
+    _call((a, w, out, ssq,), "mmada_gemm_swiglu_rownorm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(),
+              out.stride(0), ssq.data_ptr(), ssq_tiles, norm_dim, float(eps), M, N, K, cta_group)
     _timed_end(e0, rest)
     return out
 
@@ -146,9 +165,9 @@ def gemm_qkv_rope_rownorm(a: torch.Tensor, wqkv: torch.Tensor, sin: torch.Tensor
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     e0, rest = _timed(M, N, K, 7)
-    _lib.call("mmada_gemm_qkv_rope_rownorm_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0),
+    _call((a, wqkv, out, sin, cos, ssq,), "mmada_gemm_qkv_rope_rownorm_bf16", a.data_ptr(), a.stride(0), wqkv.data_ptr(), wqkv.stride(0),
               out.data_ptr(), out.stride(0), sin.data_ptr(), cos.data_ptr(), ssq.data_ptr(), ssq_tiles, norm_dim, float(eps),
-              M, N, K, 2 * d_model, head_dim, seq_len, cta_group, _stream())
+              M, N, K, 2 * d_model, head_dim, seq_len, cta_group)
     _timed_end(e0, rest)
     return out
 
@@ -160,8 +179,8 @@ def embed_norm(ids: torch.Tensor, table: torch.Tensor, xb: torch.Tensor, ssq: to
     M, d = ids.numel(), table.shape[1]
     assert xb.shape == (M, d) and xb.is_contiguous() and ssq.numel() >= M
     out = torch.empty((M, d), dtype=torch.float32, device=ids.device)
-    _lib.call("mmada_embed_norm_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), xb.data_ptr(), ssq.data_ptr(), M, d,
-              table.shape[0], _stream())
+    _call((ids, table, out, xb, ssq,), "mmada_embed_norm_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), xb.data_ptr(), ssq.data_ptr(), M, d,
+              table.shape[0])
     return out
 
 
@@ -169,8 +188,8 @@ def embed(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     _chk(ids, torch.int64, "ids"); _chk(table, torch.bfloat16, "table")
     ids = ids.contiguous().view(-1)
     out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=ids.device)
-    _lib.call("mmada_embed_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), ids.numel(), table.shape[1],
-              table.shape[0], _stream())
+    _call((ids, table, out,), "mmada_embed_f32", ids.data_ptr(), table.data_ptr(), out.data_ptr(), ids.numel(), table.shape[1],
+              table.shape[0])
     return out
 
 
@@ -179,8 +198,8 @@ def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     _chk(rows, torch.int32, "rows")
     assert x.dim() == 2 and x.stride(1) == 1 and x.is_cuda
     out = torch.empty((rows.numel(), x.shape[1]), dtype=x.dtype, device=x.device)
-    _lib.call("mmada_gather_rows", x.data_ptr(), x.stride(0) * x.element_size(), rows.data_ptr(), out.data_ptr(),
-              rows.numel(), x.shape[1] * x.element_size(), _stream())
+    _call((x, rows, out,), "mmada_gather_rows", x.data_ptr(), x.stride(0) * x.element_size(), rows.data_ptr(), out.data_ptr(),
+              rows.numel(), x.shape[1] * x.element_size())
     return out
 
 
@@ -193,8 +212,8 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, rows: Optional[to
         _chk(rows, torch.int32, "rows")
     if out is None:
         out = torch.empty((m_out, x.shape[1]), dtype=torch.bfloat16, device=x.device)
-    _lib.call("mmada_rmsnorm_bf16", x.data_ptr(), weight.data_ptr(), out.data_ptr(), _ptr(rows), m_out, x.shape[1],
-              float(eps), _stream())
+    _call((x, weight, out, rows,), "mmada_rmsnorm_bf16", x.data_ptr(), weight.data_ptr(), out.data_ptr(), _ptr(rows), m_out, x.shape[1],
+              float(eps))
     return out
 
 
@@ -202,8 +221,8 @@ def rope_inplace(qkv: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, d_mode
     _chk(qkv, torch.bfloat16, "qkv"); _chk(sin, torch.float32, "sin"); _chk(cos, torch.float32, "cos")
     assert qkv.dim() == 2 and qkv.stride(1) == 1 and sin.is_contiguous() and cos.is_contiguous()
     assert sin.shape[-1] == head_dim // 2 and sin.shape[0] >= seq_len
-    _lib.call("mmada_rope_inplace_bf16", qkv.data_ptr(), qkv.stride(0), sin.data_ptr(), cos.data_ptr(), qkv.shape[0],
-              d_model, head_dim, seq_len, _stream())
+    _call((qkv, sin, cos,), "mmada_rope_inplace_bf16", qkv.data_ptr(), qkv.stride(0), sin.data_ptr(), cos.data_ptr(), qkv.shape[0],
+              d_model, head_dim, seq_len)
     return qkv
 
 
@@ -216,8 +235,15 @@ def attention(qkv: torch.Tensor, batch: int, seq_len: int, n_heads: int, head_di
     if out is None:
         out = torch.empty((batch * seq_len, d), dtype=torch.bfloat16, device=qkv.device)
     es = qkv.element_size()
-    _lib.call("mmada_attention_bf16", qkv.data_ptr(), qkv.data_ptr() + d * es, qkv.data_ptr() + 2 * d * es, qkv.stride(0),
-              out.data_ptr(), out.stride(0), batch, seq_len, n_heads, head_dim, 1.0 / math.sqrt(head_dim), _stream())
+    ev = ATT_EVENTS
+    if ev is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _call((qkv, out,), "mmada_attention_bf16", qkv.data_ptr(), qkv.data_ptr() + d * es, qkv.data_ptr() + 2 * d * es, qkv.stride(0),
+              out.data_ptr(), out.stride(0), batch, seq_len, n_heads, head_dim, 1.0 / math.sqrt(head_dim))
+    if ev is not None:
+        e1.record()
+        ev.append((e0, e1, batch, seq_len, n_heads, head_dim))
     return out
 
 
@@ -255,10 +281,10 @@ def t2i_sample_step(cond: torch.Tensor, uncond: Optional[torch.Tensor], q: torch
     masking = torch.empty((B, N), dtype=torch.uint8, device=cond.device) if want_masking else None
     raw = torch.empty((B, N), dtype=torch.int64, device=cond.device) if want_raw else None
     # python scalars reach the tensor op as fp32 in the reference ((1 + g) * cond, g * uncond, T * gumbel)
-    _lib.call("mmada_t2i_sample_step", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
+    _call((cond, uncond, q, u, known, input_ids, sampled, sel, masking, raw, tickets,), "mmada_t2i_sample_step", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
               _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking), _ptr(raw),
               1 if no_remask else 0, tickets.data_ptr(), B, N, C, float(1 + guidance), float(guidance),
-              float(mask_len_raw), float(temperature), mask_id, text_vocab, _stream())
+              float(mask_len_raw), float(temperature), mask_id, text_vocab)
     if want_raw:
         return sampled, sel, (masking.bool() if want_masking else None), raw
     return sampled, sel, (masking.bool() if want_masking else None)
@@ -285,10 +311,10 @@ def _t2i_sample_step_compact(cond, uncond, q, u, known, input_ids, img_off, tick
     sampled = torch.empty((B, N), dtype=torch.int64, device=cond.device)
     sel = torch.empty((B, N), dtype=torch.float32, device=cond.device)
     masking = torch.empty((B, N), dtype=torch.uint8, device=cond.device) if want_masking else None
-    _lib.call("mmada_t2i_sample_step_compact", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
+    _call((cond, uncond, q, u, known, input_ids, sampled, sel, masking, tickets, slot,), "mmada_t2i_sample_step_compact", cond.data_ptr(), _ptr(uncond), q.data_ptr(), u.data_ptr(), known.data_ptr(),
               _ptr(input_ids), ld_ids, img_off, sampled.data_ptr(), sel.data_ptr(), _ptr(masking),
               1 if no_remask else 0, tickets.data_ptr(), B, N, C, float(1 + guidance), float(guidance),
-              float(mask_len_raw), float(temperature), mask_id, text_vocab, slot.data_ptr(), _stream())
+              float(mask_len_raw), float(temperature), mask_id, text_vocab, slot.data_ptr())
     return sampled, sel, (masking.bool() if want_masking else None)
 
 
@@ -301,8 +327,8 @@ def compact_masked_rows(known: torch.Tensor, L: int, img_off: int, cap: int, bra
     assert known.is_contiguous()
     rows = torch.empty(branches * B * cap, dtype=torch.int32, device=known.device)
     slot = torch.empty((B, N), dtype=torch.int32, device=known.device)
-    _lib.call("mmada_compact_masked_rows", known.data_ptr(), rows.data_ptr(), slot.data_ptr(), B, N, L, img_off, cap,
-              branches, mask_id, _stream())
+    _call((known, rows, slot,), "mmada_compact_masked_rows", known.data_ptr(), rows.data_ptr(), slot.data_ptr(), B, N, L, img_off, cap,
+              branches, mask_id)
     return rows, slot
 
 
@@ -312,8 +338,8 @@ def mask_by_random_topk(mask_len: torch.Tensor, probs: torch.Tensor, u: torch.Te
     ml = mask_len.to(device=probs.device).long().reshape(-1).contiguous()
     assert ml.numel() == B
     out = torch.empty((B, N), dtype=torch.uint8, device=probs.device)
-    _lib.call("mmada_mask_by_random_topk", probs.contiguous().data_ptr(), u.contiguous().data_ptr(), ml.data_ptr(),
-              out.data_ptr(), B, N, float(temperature), _stream())
+    _call((probs, u, ml, out,), "mmada_mask_by_random_topk", probs.contiguous().data_ptr(), u.contiguous().data_ptr(), ml.data_ptr(),
+              out.data_ptr(), B, N, float(temperature))
     return out.bool()
 
 
@@ -331,8 +357,8 @@ def text_sample_rows(logits: torch.Tensor, un_logits: Optional[torch.Tensor], cf
         assert u_noise.is_contiguous() and u_noise.shape == logits.shape
     x0 = torch.empty(R, dtype=torch.int64, device=logits.device)
     conf = torch.empty(R, dtype=torch.float64, device=logits.device)
-    _lib.call("mmada_text_sample_rows", logits.data_ptr(), _ptr(un_logits), float(cfg_scale + 1), _ptr(u_noise),
-              int(seed) & 0xFFFFFFFFFFFFFFFF, float(temperature), R, V, x0.data_ptr(), conf.data_ptr(), _stream())
+    _call((logits, un_logits, u_noise, x0, conf,), "mmada_text_sample_rows", logits.data_ptr(), _ptr(un_logits), float(cfg_scale + 1), _ptr(u_noise),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, float(temperature), R, V, x0.data_ptr(), conf.data_ptr())
     return x0, conf
 
 
@@ -340,7 +366,7 @@ def block_mask_count(x: torch.Tensor, lo: int, block: int, mask_id: int) -> torc
     _chk(x, torch.int64, "x")
     assert x.dim() == 2 and x.stride(1) == 1
     cnt = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)
-    _lib.call("mmada_block_mask_count", x.data_ptr(), x.stride(0), lo, block, x.shape[0], mask_id, cnt.data_ptr(), _stream())
+    _call((x, cnt,), "mmada_block_mask_count", x.data_ptr(), x.stride(0), lo, block, x.shape[0], mask_id, cnt.data_ptr())
     return cnt
 
 
@@ -356,8 +382,8 @@ def text_transfer(x: torch.Tensor, lo: int, block: int, x0: torch.Tensor, conf: 
         _chk(conf_override, torch.float64, "conf_override")
         assert conf_override.is_contiguous() and conf_override.numel() == B * block
     tr = torch.empty((B, block), dtype=torch.uint8, device=x.device) if want_transfer else None
-    _lib.call("mmada_text_transfer", x.data_ptr(), x.stride(0), lo, block, x0.data_ptr(), _ptr(conf), _ptr(conf_override),
-              cnt.data_ptr(), steps, step, B, mask_id, _ptr(tr), _stream())
+    _call((x, x0, conf, conf_override, cnt, tr,), "mmada_text_transfer", x.data_ptr(), x.stride(0), lo, block, x0.data_ptr(), _ptr(conf), _ptr(conf_override),
+              cnt.data_ptr(), steps, step, B, mask_id, _ptr(tr))
     return tr.bool() if want_transfer else None
 
 
@@ -374,8 +400,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, taps: i
     if resid is not None:
         _chk(resid, torch.float32, "resid")
         assert resid.is_contiguous() and resid.shape == out.shape
-    _lib.call("mmada_conv_nhwc_bf16", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(resid), B, H, W,
-              Cin, Cout, taps, epilogue, _stream())
+    _call((x, weight, bias, out, resid,), "mmada_conv_nhwc_bf16", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(resid), B, H, W,
+              Cin, Cout, taps, epilogue)
     return out
 
 
@@ -383,8 +409,8 @@ def lfq_decode_nhwc(indices: torch.Tensor, pq_weight: torch.Tensor, pq_bias: tor
     _chk(indices, torch.int64, "indices")
     B = indices.shape[0]
     out = torch.empty((B, h, w, 64), device=indices.device, dtype=torch.bfloat16)
-    _lib.call("mmada_lfq_decode_nhwc", indices.contiguous().data_ptr(), pq_weight.data_ptr(), pq_bias.data_ptr(),
-              out.data_ptr(), indices.numel(), _stream())
+    _call((indices, pq_weight, pq_bias, out,), "mmada_lfq_decode_nhwc", indices.contiguous().data_ptr(), pq_weight.data_ptr(), pq_bias.data_ptr(),
+              out.data_ptr(), indices.numel())
     return out
 
 
@@ -392,7 +418,7 @@ def lfq_indices_to_bits(indices: torch.Tensor) -> torch.Tensor:
     _chk(indices, torch.int64, "indices")
     B, N = indices.shape
     out = torch.empty((B, 13, N), device=indices.device, dtype=torch.float32)
-    _lib.call("mmada_lfq_indices_to_bits", indices.contiguous().data_ptr(), out.data_ptr(), B, N, _stream())
+    _call((indices, out,), "mmada_lfq_indices_to_bits", indices.contiguous().data_ptr(), out.data_ptr(), B, N)
     return out
 
 
@@ -400,7 +426,7 @@ def lfq_bits_to_indices(z: torch.Tensor) -> torch.Tensor:
     _chk(z, torch.float32, "z")
     B, N = z.shape[0], z[0, 0].numel()
     out = torch.empty((B, N), device=z.device, dtype=torch.int64)
-    _lib.call("mmada_lfq_bits_to_indices", z.contiguous().data_ptr(), out.data_ptr(), B, N, _stream())
+    _call((z, out,), "mmada_lfq_bits_to_indices", z.contiguous().data_ptr(), out.data_ptr(), B, N)
     return out
 
 
@@ -411,9 +437,9 @@ def groupnorm_swish(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, su
     B, H, W, C = x.shape
     assert x.is_contiguous() and sums.dtype == torch.float64 and sums.numel() >= B * 64
     out = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_groupnorm_stats", x.data_ptr(), sums.data_ptr(), B, H * W, C, _stream())
-    _lib.call("mmada_groupnorm_apply_bf16", x.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-              B, H * W, C, float(eps), 1 if swish else 0, _stream())
+    _call((x, sums,), "mmada_groupnorm_stats", x.data_ptr(), sums.data_ptr(), B, H * W, C)
+    _call((x, sums, gamma, beta, out,), "mmada_groupnorm_apply_bf16", x.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+              B, H * W, C, float(eps), 1 if swish else 0)
     return out
 
 
@@ -421,14 +447,14 @@ def upsample2x_nhwc(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     B, H, W, C = x.shape
     out = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_upsample2x_nhwc_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    _call((x, out,), "mmada_upsample2x_nhwc_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C)
     return out
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_cast_f32_bf16", x.contiguous().data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _call((x, out,), "mmada_cast_f32_bf16", x.contiguous().data_ptr(), out.data_ptr(), x.numel())
     return out
 
 
@@ -436,7 +462,7 @@ def softmax_rows_bf16(x: torch.Tensor, scale: float) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     R, n = x.shape
     out = torch.empty((R, n), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_softmax_rows_bf16", x.contiguous().data_ptr(), out.data_ptr(), R, n, float(scale), _stream())
+    _call((x, out,), "mmada_softmax_rows_bf16", x.contiguous().data_ptr(), out.data_ptr(), R, n, float(scale))
     return out
 
 
@@ -444,14 +470,14 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     B, H, W, C = x.shape
     out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
-    _lib.call("mmada_nhwc_to_nchw_f32", x.contiguous().data_ptr(), out.data_ptr(), B, H * W, C, _stream())
+    _call((x, out,), "mmada_nhwc_to_nchw_f32", x.contiguous().data_ptr(), out.data_ptr(), B, H * W, C)
     return out
 
 
 def image_to_uint8(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
-    _lib.call("mmada_image_to_uint8", x.contiguous().data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _call((x, out,), "mmada_image_to_uint8", x.contiguous().data_ptr(), out.data_ptr(), x.numel())
     return out
 
 
@@ -461,7 +487,7 @@ def image_to_nhwc64(pixel_values: torch.Tensor) -> torch.Tensor:
     B, C, H, W = pixel_values.shape
     assert C == 3
     out = torch.empty((B, H, W, 64), device=pixel_values.device, dtype=torch.bfloat16)
-    _lib.call("mmada_image_to_nhwc64_bf16", pixel_values.contiguous().data_ptr(), out.data_ptr(), B, H, W, _stream())
+    _call((pixel_values, out,), "mmada_image_to_nhwc64_bf16", pixel_values.contiguous().data_ptr(), out.data_ptr(), B, H, W)
     return out
 
 
@@ -471,7 +497,7 @@ def space_to_depth2(x: torch.Tensor) -> torch.Tensor:
     B, H, W, C = x.shape
     assert x.is_contiguous()
     out = torch.empty((B, H // 2, W // 2, 4 * C), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_space_to_depth2_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C, _stream())
+    _call((x, out,), "mmada_space_to_depth2_bf16", x.data_ptr(), out.data_ptr(), B, H, W, C)
     return out
 
 
@@ -481,13 +507,12 @@ def conv1d_gather(x: torch.Tensor, taps: int, dilation: int = 1, upsample: int =
     B, T, C = x.shape
     assert x.is_contiguous()
     out = torch.empty((B, T * upsample, taps * C), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mmada_conv1d_gather_bf16", x.data_ptr(), out.data_ptr(), B, T, C, taps, dilation, upsample, 1 if relu else 0,
-              _stream())
+    _call((x, out,), "mmada_conv1d_gather_bf16", x.data_ptr(), out.data_ptr(), B, T, C, taps, dilation, upsample, 1 if relu else 0)
     return out
 
 
 def relu_(x: torch.Tensor) -> torch.Tensor:
     _chk(x, torch.float32, "x")
     assert x.is_contiguous()
-    _lib.call("mmada_relu_f32", x.data_ptr(), x.numel(), _stream())
+    _call((x,), "mmada_relu_f32", x.data_ptr(), x.numel())
     return x

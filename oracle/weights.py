@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import hashlib
 import math
+from collections.abc import Mapping
 from typing import Dict
 
 import torch
@@ -53,32 +54,81 @@ def _gen(seed: int, name: str) -> torch.Generator:
     return g
 
 
-def _normal(seed: int, name: str, shape, std: float, dtype=torch.float32) -> torch.Tensor:
-    t = torch.randn(shape, generator=_gen(seed, name), dtype=torch.float32)
+def _normal(seed: int, name: str, shape, std: float, dtype=torch.float32, device="cpu") -> torch.Tensor:
+    """Truncated normal from the (seed, name) generator.  ``device`` other than the CPU draws on that device from a
+    generator with the same seed: same rule, different (device-specific) values — only for cases without goldens."""
+    device = torch.device(device)
+    if device.type == "cpu":
+        t = torch.randn(shape, generator=_gen(seed, name), dtype=torch.float32)
+    else:
+        g = torch.Generator(device=device)
+        g.manual_seed(_gen(seed, name).initial_seed())
+        t = torch.randn(shape, generator=g, dtype=torch.float32, device=device)
     t.clamp_(-3.0, 3.0).mul_(std)
     return t.to(dtype)
 
 
-def make_llada_weights(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
-    """State dict with the reference's key names for ``cfg`` (no biases, untied head)."""
-    d, ffn, V = cfg["d_model"], cfg["mlp_hidden_size"], cfg["vocab_size"]
-    sd: Dict[str, torch.Tensor] = {}
+def llada_weight_keys(cfg: dict):
+    """State-dict key names of the reference model for ``cfg``, in load order."""
     p = "model.transformer."
-    sd[p + "wte.weight"] = _normal(seed, "wte", (V, d), 1.0 / math.sqrt(d), dtype)
+    keys = [p + "wte.weight"]
     for i in range(cfg["n_layers"]):
         b = f"{p}blocks.{i}."
-        res = 1.0 / math.sqrt(2 * (i + 1))
-        sd[b + "attn_norm.weight"] = (1.0 + _normal(seed, b + "attn_norm", (d,), 0.1)).to(dtype)
-        sd[b + "ff_norm.weight"] = (1.0 + _normal(seed, b + "ff_norm", (d,), 0.1)).to(dtype)
-        for n in ("q_proj", "k_proj", "v_proj"):
-            sd[b + n + ".weight"] = _normal(seed, b + n, (d, d), 1.0 / math.sqrt(d), dtype)
-        sd[b + "attn_out.weight"] = _normal(seed, b + "attn_out", (d, d), res / math.sqrt(d), dtype)
-        sd[b + "ff_proj.weight"] = _normal(seed, b + "ff_proj", (ffn, d), 1.0 / math.sqrt(d), dtype)
-        sd[b + "up_proj.weight"] = _normal(seed, b + "up_proj", (ffn, d), 1.0 / math.sqrt(d), dtype)
-        sd[b + "ff_out.weight"] = _normal(seed, b + "ff_out", (d, ffn), res / math.sqrt(ffn), dtype)
-    sd[p + "ln_f.weight"] = (1.0 + _normal(seed, "ln_f", (d,), 0.1)).to(dtype)
-    sd[p + "ff_out.weight"] = _normal(seed, "head", (V, d), 1.0 / math.sqrt(d), dtype)
-    return sd
+        keys += [b + n + ".weight" for n in ("attn_norm", "ff_norm", "q_proj", "k_proj", "v_proj", "attn_out", "ff_proj",
+                                             "up_proj", "ff_out")]
+    return keys + [p + "ln_f.weight", p + "ff_out.weight"]
+
+
+def llada_weight(cfg: dict, seed: int, key: str, dtype=torch.float32, device="cpu") -> torch.Tensor:
+    """ONE tensor of ``make_llada_weights(cfg, seed)`` by its state-dict key (same values on the CPU)."""
+    d, ffn, V = cfg["d_model"], cfg["mlp_hidden_size"], cfg["vocab_size"]
+    p = "model.transformer."
+    if key == p + "wte.weight":
+        return _normal(seed, "wte", (V, d), 1.0 / math.sqrt(d), dtype, device)
+    if key == p + "ln_f.weight":
+        return (1.0 + _normal(seed, "ln_f", (d,), 0.1, device=device)).to(dtype)
+    if key == p + "ff_out.weight":
+        return _normal(seed, "head", (V, d), 1.0 / math.sqrt(d), dtype, device)
+    assert key.startswith(p + "blocks.") and key.endswith(".weight"), key
+    i, n = key[len(p + "blocks."):-len(".weight")].split(".")
+    i = int(i)
+    b = f"{p}blocks.{i}."
+    res = 1.0 / math.sqrt(2 * (i + 1))
+    if n in ("attn_norm", "ff_norm"):
+        return (1.0 + _normal(seed, b + n, (d,), 0.1, device=device)).to(dtype)
+    shape, std = {"q_proj": ((d, d), 1.0 / math.sqrt(d)), "k_proj": ((d, d), 1.0 / math.sqrt(d)),
+                  "v_proj": ((d, d), 1.0 / math.sqrt(d)), "attn_out": ((d, d), res / math.sqrt(d)),
+                  "ff_proj": ((ffn, d), 1.0 / math.sqrt(d)), "up_proj": ((ffn, d), 1.0 / math.sqrt(d)),
+                  "ff_out": ((d, ffn), res / math.sqrt(ffn))}[n]
+    return _normal(seed, b + n, shape, std, dtype, device)
+
+
+class LazyLladaWeights(Mapping):
+    """``make_llada_weights`` as a lazy mapping: a tensor is generated when it is read and not kept, so an 8B-parameter
+    state dict (32 GB in fp32) can be streamed layer by layer (tests/test_full_size_gpu.py)."""
+
+    def __init__(self, cfg: dict, seed: int = 0, dtype=torch.float32, device="cpu"):
+        self.cfg, self.seed, self.dtype, self.device = cfg, seed, dtype, device
+        self._keys = llada_weight_keys(cfg)
+
+    def __getitem__(self, key: str) -> torch.Tensor:
+        return llada_weight(self.cfg, self.seed, key, self.dtype, self.device)
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def block(self, i: int) -> Dict[str, torch.Tensor]:
+        """The nine tensors of block ``i``, materialised."""
+        b = f"model.transformer.blocks.{i}."
+        return {k: self[k] for k in self._keys if k.startswith(b)}
+
+
+def make_llada_weights(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """State dict with the reference's key names for ``cfg`` (no biases, untied head)."""
+    return {k: llada_weight(cfg, seed, k, dtype) for k in llada_weight_keys(cfg)}
 
 
 def make_t2i_prompts(batch: int, prefix_len: int, n_img: int, seed: int = 0, mask_id: int = 126336):
