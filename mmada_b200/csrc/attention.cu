@@ -421,6 +421,9 @@ static int dispatch_attention(const void* q, const void* k, const void* v, int64
     }
 }
 
+// attention_duo.cu: persistent, two query tiles per CTA in ping-pong, one thread per query row, head_dim 128
+int launch_attention_duo(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                         int Lq, int H, float scale, int poly, cudaStream_t stream);
 // attention_pair.cu: persistent CTA pairs, head_dim 128
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream);
@@ -449,7 +452,9 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
             // (batch, head), a second launch on the same stream) and the pair kernel walks whole items only:
             // worth it once the extra items would cost the pairs a wave of their own.
             static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
+            static const int use_duo = experiment_env("MMADA_ATT_DUO", 1);      // 0: the round-1 pair kernel (A/B runs)
             auto pair = [&](int Lq) {
+                if (use_duo) return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
             };
             const int rem = L % 256;

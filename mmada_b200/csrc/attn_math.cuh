@@ -41,8 +41,8 @@ __device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {     // round to
 // polynomial of 2^f on [0,1), exponent patched in with an integer multiply-add.  Relative error ~1e-4 —
 // P is rounded to bf16 (2^-9) anyway.
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
-    x.x = fmaxf(x.x, -126.0f);
-    x.y = fmaxf(x.y, -126.0f);
+    x.x = fminf(fmaxf(x.x, -126.0f), 127.0f);       // above 2^127 the exponent patch would wrap: saturate (callers that
+    x.y = fminf(fmaxf(x.y, -126.0f), 127.0f);       // speculate on the range detect 2^127 in their row sums)
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
     const float2 r = fadd2_rm(x, magic);
     const float2 fl = fadd2(r, nmagic);                                   // floor(x), exact
