@@ -93,12 +93,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 // Waits of warps that are off the critical path (epilogue, TMA producer with a deep ring): sleep between polls, so the
 // polling does not compete with the MUFU instructions of the warps that share the scheduler (both go through the
 // MIO queue)
+// try_wait with a suspend-time hint (ns): the thread is suspended by the hardware until the phase completes or the hint
+// expires, instead of returning after the (short) default limit — a waiting warp then issues a handful of instructions
+// per wait instead of polling in the issue slots of the warps that share its scheduler
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return done != 0;
+}
 // Blocking wait without a function call (a call into the out-of-line watchdog keeps ptxas from giving the calling region
 // more registers than the kernel-wide cap after setmaxnreg.inc): bounded spin, traps without a message.
 __device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
     uint32_t n = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++n > (1u << 26)) __trap();         // each failed try_wait already suspends for a while: seconds in total
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++n > (1u << 22)) __trap();         // each failed try_wait suspends for up to the hint: seconds in total
     }
 }
 static __device__ __noinline__ void mbar_wait_backoff_slow(uint32_t bar, uint32_t parity, int tag, unsigned ns) {

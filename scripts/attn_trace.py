@@ -6,7 +6,7 @@ Columns per key tile g of CTA 0 (clocks since the first event):
 import ctypes, sys, os
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-lib = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "..", "mmada_b200", "csrc", "build", "libattn_trace.so"))
+lib = ctypes.CDLL(os.path.join(os.path.dirname(__file__), "..", "mmada_b200", "csrc", "build", os.environ.get("ATT_TRACE_LIB", "libattn_trace.so")))
 B, L, H, hd = 16, 1539, 32, 128
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B * L, 3 * H * hd, device="cuda", generator=g).bfloat16()
