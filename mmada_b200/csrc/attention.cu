@@ -424,9 +424,14 @@ static int dispatch_attention(const void* q, const void* k, const void* v, int64
 // attention_duo.cu: persistent, two query tiles per CTA in ping-pong, one thread per query row, head_dim 128
 int launch_attention_duo(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                          int Lq, int H, float scale, int poly, cudaStream_t stream);
-// attention_pair.cu: persistent CTA pairs, head_dim 128
+#ifdef MMADA_EXPERIMENTS
+// EXPERIMENTS builds only (A/B runs): attention_quad.cu = CTA pairs with two 256-row query blocks in
+// flight and P through shared memory; attention_pair.cu = round 1's pair kernel
+int launch_attention_quad(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                          int Lq, int H, float scale, int poly, cudaStream_t stream);
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream);
+#endif
 
 }  // namespace mmada
 
@@ -445,25 +450,28 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
         return kBadArgument;
     cudaStream_t s = (cudaStream_t)stream;
     if (head_dim == 128) {
-        static const int use_pair = experiment_env("MMADA_ATT_PAIR", 1);        // 0: single-CTA kernel (A/B runs)
-        if (use_pair && L > 128) {
-            // A pair item is 256 query rows.  When the last item of every (batch, head) would hold at most one
-            // 128-row tile (L = 1539: 3 rows), those rows go to the single-CTA kernel instead (one CTA per
-            // (batch, head), a second launch on the same stream) and the pair kernel walks whole items only:
-            // worth it once the extra items would cost the pairs a wave of their own.
-            static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
-            static const int use_duo = experiment_env("MMADA_ATT_DUO", 1);      // 0: the round-1 pair kernel (A/B runs)
-            auto pair = [&](int Lq) {
-                if (use_duo) return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
-                return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
+        if (L > 128) {
+            // The persistent kernel walks items of 256 query rows.  When the last item of every (batch, head) would hold at
+            // most one 128-row tile (L = 1539: 3 rows), those rows go to the single-CTA kernel instead (one CTA per
+            // (batch, head), a second launch on the same stream) and the persistent kernel walks whole items only:
+            // worth it once the extra items would cost a wave of their own.
+            auto main_kernel = [&](int Lq) {
+#ifdef MMADA_EXPERIMENTS
+                // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu (the product's), 2 attention_quad.cu
+                static const int which = experiment_env("MMADA_ATT_KERNEL", 1);
+                if (which == 2) return launch_attention_quad(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
+                if (which == 0) return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
+#endif
+                return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
             };
+            static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
             const int rem = L % 256;
             if (split_tail && L > 256 && rem > 0 && rem <= 128 && B * H >= num_sms()) {
-                const int st = pair(L - rem);
+                const int st = main_kernel(L - rem);
                 if (st) return st;
                 return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, L - rem, s);
             }
-            return pair(L);
+            return main_kernel(L);
         }
         return dispatch_attention<128>(q, k, v, ld, out, ldo, B, L, H, scale, 0, s);
     }

@@ -412,14 +412,18 @@ attention_duo_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll 1
                     for (;;) {
                         if (need_max) {
+                            // (z is an opaque zero defined inside this branch: OR-ing it into the operands keeps ptxas from
+                            // hoisting the ~90 FMNMX of the maximum pass above the test, where every tile would pay for them)
+                            uint32_t z;
+                            asm volatile("mov.u32 %0, 0;" : "=r"(z));
                             float mxa[8];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) mxa[u] = fmaxf(__uint_as_float(sv[2 * u]), __uint_as_float(sv[2 * u + 1]));
+                            for (int u = 0; u < 8; ++u) mxa[u] = fmaxf(__uint_as_float(sv[2 * u] | z), __uint_as_float(sv[2 * u + 1] | z));
 #pragma unroll
                             for (int i = 16; i < 128; i += 16)
 #pragma unroll
                                 for (int u = 0; u < 8; ++u)
-                                    mxa[u] = fmaxf(mxa[u], fmaxf(__uint_as_float(sv[i + 2 * u]), __uint_as_float(sv[i + 2 * u + 1])));
+                                    mxa[u] = fmaxf(mxa[u], fmaxf(__uint_as_float(sv[i + 2 * u] | z), __uint_as_float(sv[i + 2 * u + 1] | z)));
                             const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                                                    fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
                             const float m_new = fmaxf(m_used, mx);

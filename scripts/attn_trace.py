@@ -13,6 +13,7 @@ qkv = torch.randn(B * L, 3 * H * hd, device="cuda", generator=g).bfloat16()
 out = torch.empty(B * L, H * hd, device="cuda", dtype=torch.bfloat16)
 trace = torch.zeros(4 * 64 * 8, dtype=torch.int64, device="cuda")
 lib.mmada_attention_duo_set_trace(ctypes.c_void_p(trace.data_ptr()))
+lib.mmada_attention_quad_set_trace(ctypes.c_void_p(trace.data_ptr()))
 f = lib.mmada_attention_bf16
 f.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
 d = H * hd
@@ -26,4 +27,4 @@ t0 = int(tr[tr > 0].min())
 print("g | softmax0: wait sready loaded max exp arrived ofull epi_done | softmax1: ... | mma0: pv_wait pv_ready pv_issued s_ready s_issued | mma1: ...")
 for t in range(int(sys.argv[1]) if len(sys.argv) > 1 else 42):
     r = lambda role, evs: " ".join(f"{int(tr[role, t, e]) - t0:7d}" if tr[role, t, e] > 0 else "      -" for e in evs)
-    print(f"{t:2d} | {r(0, range(8))} | {r(1, range(8))} | {r(2, range(5))} | {r(3, range(5))}")
+    print(f"{t:2d} | {r(0, range(8))} | {r(1, range(6))} | {r(2, range(5))} | {r(3, range(5))}")
