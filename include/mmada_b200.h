@@ -209,6 +209,20 @@ int mmada_conv1d_gather_bf16(const float* x, void* out_bf16, int B, int T_in, in
                              int upsample, int relu, void* stream);
 int mmada_relu_f32(float* x, int64_t n, void* stream);
 
+/* Sequence assembly of the generation tasks (UniversalPrompting, training/prompting_utils.py).  text: every row's
+ * pre-tokenised text ids concatenated, text_off [B+1] offsets; body [B,N] image / motion tokens (row pitch ld_body).
+ * A text gets `bos` in front unless it starts with it (an empty text becomes [bos]).
+ * mode 0 (t2i_gen_prompt :200-233; t2m_prompt :87-144 without conditional drop-out): ids [B, text_slots + N + 2] =
+ *   [pad.. task bos text eos] (text_slots = the class's max_text_len + 1 ids, left-padded; a longer text is cut to
+ *   text_slots - 1 ids + eos) open body close;  mask [B, L] = 0 on the padding, 1 elsewhere.
+ * mode 1 (mmu_gen_prompt :379-425): ids [B, 3 + N + text_slots] = task open body close [bos text eos, eos..] (text_slots =
+ *   the class's max_text_len; cut to text_slots - 1 ids + eos);  mask [B] = prompt_length: the head plus the text up to
+ *   and including its last `end_header` token (:401-413).                                                         */
+int mmada_build_prompts(const int64_t* text, const int64_t* text_off, const int64_t* body, int64_t ld_body, int64_t* ids,
+                        int64_t* mask, int B, int N, int text_slots, int mode, int64_t task_token, int64_t bos,
+                        int64_t eos, int64_t pad, int64_t open_token, int64_t close_token, int64_t end_header,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

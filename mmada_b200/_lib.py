@@ -57,6 +57,7 @@ SIGNATURES = {
     "mmada_space_to_depth2_bf16": [_p, _p, _i, _i, _i, _i, _p],
     "mmada_conv1d_gather_bf16": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mmada_relu_f32": [_p, _i64, _p],
+    "mmada_build_prompts": [_p, _p, _p, _i64, _p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p],
 }
 
 

@@ -516,3 +516,21 @@ def relu_(x: torch.Tensor) -> torch.Tensor:
     assert x.is_contiguous()
     _call((x,), "mmada_relu_f32", x.data_ptr(), x.numel())
     return x
+
+
+def build_prompts(text: torch.Tensor, text_off: torch.Tensor, body: torch.Tensor, text_slots: int, mode: int, task: int,
+                  bos: int, eos: int, pad: int, open_tok: int, close_tok: int, end_header: int = -1):
+    """Sequence assembly on the device (csrc/prompting.cu, mmada_build_prompts).  text int64 [sum of lengths], text_off
+    int64 [B+1], body int64 [B, N].  mode 0 -> (ids [B, text_slots+N+2], attention mask [B, L]); mode 1 -> (ids
+    [B, 3+N+text_slots], prompt lengths [B])."""
+    _chk(text, torch.int64, "text"); _chk(text_off, torch.int64, "text_off"); _chk(body, torch.int64, "body")
+    assert body.dim() == 2 and body.stride(1) == 1 and text.is_contiguous() and text_off.is_contiguous()
+    B, N = body.shape
+    assert text_off.numel() == B + 1
+    L = text_slots + N + 2 if mode == 0 else 3 + N + text_slots
+    ids = torch.empty((B, L), dtype=torch.int64, device=body.device)
+    mask = torch.empty((B, L) if mode == 0 else (B,), dtype=torch.int64, device=body.device)
+    _call((text, text_off, body, ids, mask,), "mmada_build_prompts", text.data_ptr(), text_off.data_ptr(), body.data_ptr(),
+          body.stride(0), ids.data_ptr(), mask.data_ptr(), B, N, int(text_slots), int(mode), int(task), int(bos), int(eos),
+          int(pad), int(open_tok), int(close_tok), int(end_header))
+    return ids, mask

@@ -275,6 +275,90 @@ def logits_case(name, cfg, B, L, wseed, seed):
           absmax=ref.abs().max(), std=ref.std(), meta=np.array([B, L, wseed, seed]))
 
 
+def prompting_case():
+    """training/prompting_utils.py (the real class, stub tokenizer) against oracle/prompting.py; stores ragged inputs and
+    the reference's outputs."""
+    import importlib.util
+    from . import prompting as OP
+    print("[prompting]")
+    spec = importlib.util.spec_from_file_location("ref_prompting_utils", os.path.join(rb.REF, "training", "prompting_utils.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    class Tok:
+        bos_token_id, eos_token_id = OP.BOS, OP.EOS
+        _special = {"<|end_header_id|>": OP.END_HEADER, "<|eot_id|>": 126348, "<|start_header_id|>": 126346}
+
+        def __init__(self):
+            self.table = {}
+
+        def __len__(self):
+            return W.TEXT_VOCAB
+
+        def convert_tokens_to_ids(self, toks):
+            return [self._special[t] for t in toks]
+
+        def __call__(self, texts, **kw):
+            return {"input_ids": [list(self.table[t]) for t in texts]}
+
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for name, mtl, N, lens in (("t2i_a", 16, 8, [0, 1, 5, 13, 14, 15, 16, 30]),      # padding, exact fit, truncation
+                                ("t2i_b", 512, 1024, [0, 7, 64, 200])):
+        with rb.quiet():
+            up = ref.UniversalPrompting(Tok(), max_text_len=mtl, use_reserved_token=True)
+        texts = [torch.randint(0, 126000, (n,), generator=g).tolist() for n in lens]
+        texts[2] = [OP.BOS] + texts[2][1:] if texts[2] else texts[2]                 # a text that already starts with bos
+        image = torch.randint(W.TEXT_VOCAB, W.TEXT_VOCAB + 8192, (len(lens), N), generator=g)
+        image[0, :] = 126336
+        ids_ref, mask_ref = up.t2i_gen_prompt([list(t) for t in texts], image)
+        # through __call__ with the stub tokenizer, as inference_t2i.py:92 does
+        up.text_tokenizer.table = {f"p{i}": t for i, t in enumerate(texts)}
+        ids_call, mask_call = up(([f"p{i}" for i in range(len(texts))], image), "t2i_gen")
+        assert torch.equal(ids_ref, ids_call) and torch.equal(mask_ref, mask_call)
+        for i, t in enumerate(texts):
+            ids_o, mask_o = OP.prefix_layout(t, image[i].tolist(), mtl, OP.RESERVED["<|t2i|>"], OP.RESERVED["<|soi|>"],
+                                             OP.RESERVED["<|eoi|>"])
+            assert ids_o == ids_ref[i].tolist() and mask_o == mask_ref[i].tolist(), (name, i)
+        # t2m layout (cond_dropout_prob = 0: inference)
+        with rb.quiet():
+            upm = ref.UniversalPrompting(Tok(), max_text_len=mtl, use_reserved_token=True, cond_dropout_prob=0.0)
+        motion = torch.randint(W.TEXT_VOCAB + 8192, W.TEXT_VOCAB + 8192 + 512, (len(lens), N), generator=g)
+        ids_m, mask_m, _ = upm.t2m_prompt([list(t) for t in texts], motion, motion.clone())
+        for i, t in enumerate(texts):
+            ids_o, mask_o = OP.prefix_layout(t, motion[i].tolist(), mtl, OP.RESERVED["<|t2m|>"], OP.RESERVED["<|som|>"],
+                                             OP.RESERVED["<|eom|>"])
+            assert ids_o == ids_m[i].tolist() and mask_o == mask_m[i].tolist(), (name, "t2m", i)
+        flat = torch.tensor([x for t in texts for x in t], dtype=torch.int64)
+        off = torch.tensor([0] + list(np.cumsum([len(t) for t in texts])), dtype=torch.int64)
+        out.update({f"{name}_text": flat, f"{name}_off": off, f"{name}_image": image, f"{name}_ids": ids_ref,
+                    f"{name}_mask": mask_ref, f"{name}_max_text_len": mtl, f"{name}_motion": motion,
+                    f"{name}_t2m_ids": ids_m, f"{name}_t2m_mask": mask_m})
+    # mmu_gen_prompt: one row per call (its prompt masks only concatenate for equal prompt lengths)
+    mtl, N = 24, 16
+    with rb.quiet():
+        up = ref.UniversalPrompting(Tok(), max_text_len=mtl, use_reserved_token=True)
+    lens = [0, 3, 10, 23, 24, 40]
+    texts = [torch.randint(0, 126000, (n,), generator=g).tolist() for n in lens]
+    texts[2][4] = OP.END_HEADER
+    texts[3][1] = OP.END_HEADER; texts[3][9] = OP.END_HEADER
+    texts[5][30] = OP.END_HEADER                                                     # beyond the truncation point
+    image = torch.randint(W.TEXT_VOCAB, W.TEXT_VOCAB + 8192, (len(lens), N), generator=g)
+    seqs, plens = [], []
+    for i, t in enumerate(texts):
+        with rb.quiet():
+            ids_ref, pm_ref = up.mmu_gen_prompt(image[i:i + 1], [list(t)])
+        seq_o, plen_o = OP.mmu_gen_layout(t, image[i].tolist(), mtl)
+        assert seq_o == ids_ref[0].tolist(), ("mmu_gen", i)
+        assert OP.mmu_gen_mask(plen_o, mtl) == pm_ref[0].tolist(), ("mmu_gen mask", i)
+        seqs.append(ids_ref[0]); plens.append(plen_o)
+    out.update({"mmu_text": torch.tensor([x for t in texts for x in t], dtype=torch.int64),
+                "mmu_off": torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int64), "mmu_image": image,
+                "mmu_ids": torch.stack(seqs), "mmu_prompt_length": torch.tensor(plens), "mmu_max_text_len": mtl,
+                "end_header": OP.END_HEADER})
+    _save("prompting", **out)
+
+
 def main():
     assert rb.available(), "needs /root/reference (build container)"
     torch.set_num_threads(os.cpu_count())
@@ -282,6 +366,7 @@ def main():
     magvit_case()
     magvit_encoder_case()
     motion_case()
+    prompting_case()
     logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
     logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
     t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)

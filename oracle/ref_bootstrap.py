@@ -22,6 +22,11 @@ import torch.nn as nn
 REF = os.environ.get("MMADA_REFERENCE", "/root/reference")
 
 
+def quiet():
+    """Context manager that swallows the reference's prints (config dumps, debugging output)."""
+    return contextlib.redirect_stdout(io.StringIO())
+
+
 def available() -> bool:
     return os.path.isfile(os.path.join(REF, "models", "modeling_mmada.py"))
 
