@@ -487,10 +487,18 @@ def run_own(args):
     clocks = sampler.stop()
     images = B * world * K / STEPS_PER_IMAGE
     value = images / (ms / 1e3)
+    # host cost of ENQUEUING one denoising step with an empty launch queue (the timed loop above fills the queue and then
+    # blocks on it, so its wall time follows the device): if this is well below ms_per_step the loop is not launch-bound
+    torch.cuda.synchronize()
+    t_h = time.perf_counter()
+    generation(cond_h.to(dev), unc_d, stop=1)
+    host_step_ms = (time.perf_counter() - t_h) * 1e3
+    torch.cuda.synchronize()
     gemm_ms = sum(a.elapsed_time(b) for a, b, *_ in gemm_events) if gemm_events else None
     att_ms = sum(a.elapsed_time(b) for a, b, *_ in att_events) if att_events else None
     mine = {"rank": rank, "ms_per_step": ms_own / K, "gemm_ms_per_step": None if gemm_ms is None else gemm_ms / K,
-            "attention_ms_per_step": None if att_ms is None else att_ms / K, "host_enqueue_ms_per_step": host_enqueue_ms / K,
+            "attention_ms_per_step": None if att_ms is None else att_ms / K, "host_enqueue_ms_per_step_queue_full": host_enqueue_ms / K,
+            "host_enqueue_ms_per_step_queue_empty": host_step_ms,
             "sm_mhz": clocks.get("sm_mhz"), "power_w_max": clocks.get("power_w_max"), "reasons": clocks.get("reasons")}
     per_rank = [mine]
     if world > 1:

@@ -204,6 +204,23 @@ class LLaDAModelLM:
             self.load_block(sd, i)
         return self
 
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda", torch_dtype=None, fused_norm: Optional[bool] = None, **_ignored):
+        """``MMadaModelLM.from_pretrained(dir, torch_dtype=torch.bfloat16)`` (reference inference_t2i.py:69): reads
+        ``config.json`` (the reference's ModelConfig / MMadaConfig fields; unsupported options raise) and the (sharded)
+        safetensors or ``pytorch_model.bin`` with the reference's key names, streaming one tensor at a time.  The
+        kernels compute in bf16 with an fp32 residual stream whatever ``torch_dtype`` says."""
+        from .checkpoint import ShardedCheckpoint, read_config
+        cfg = read_config(path)
+        config = cls._config_class().from_dict(cfg)
+        model = cls(config, device=device, fused_norm=fused_norm)
+        model.hf_config = cfg                              # codebook_size, num_vq_tokens, llm_vocab_size, ... as stored
+        return model.load_state_dict(ShardedCheckpoint(path))
+
+    @staticmethod
+    def _config_class():
+        return LLaDAConfig
+
     def init_random(self, seed: int = 0, std_scale: float = 1.0) -> "LLaDAModelLM":
         """Random weights generated on the device (benchmarks; no checkpoint is available offline).
         Scales follow the reference's 'mitchell' init (modeling_llada.py:106-110)."""

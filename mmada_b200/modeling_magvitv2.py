@@ -165,6 +165,15 @@ class MAGVITv2:
                 self._norm(sd, "norm_out"); self._conv(sd, key)
         return self
 
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda", **_ignored) -> "MAGVITv2":
+        """``MAGVITv2.from_pretrained(dir)`` (reference inference_t2i.py:67): ``config.json`` (the reference's class takes
+        no configuration arguments — the architecture is fixed, models/modeling_magvitv2.py:403-411) and
+        ``pytorch_model.safetensors`` | ``pytorch_model.bin`` (models/modeling_utils.py:47-49) with ``encoder.*`` /
+        ``decoder.*`` keys."""
+        from .checkpoint import ShardedCheckpoint
+        return cls(device=device).load_state_dict(ShardedCheckpoint(path))
+
     def init_random(self, seed: int = 0) -> "MAGVITv2":
         """Random decoder weights on the device (benchmarks: the checkpoint is not available offline)."""
         g = torch.Generator(device=self.device).manual_seed(seed)

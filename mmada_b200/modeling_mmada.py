@@ -30,6 +30,10 @@ class MMadaConfig(LLaDAConfig):
 
 
 class MMadaModelLM(LLaDAModelLM):
+    @staticmethod
+    def _config_class():
+        return MMadaConfig
+
     # ------------------------------------------------------------------------------------------
     def _t2i_steps(self, input_ids, uncond_input_ids, temperature, timesteps, guidance_scale, noise_schedule, generator,
                    seq_len, mask_token_id, resolution, codebook_size, kwargs):

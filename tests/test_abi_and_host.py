@@ -90,6 +90,15 @@ def test_torch_custom_ops_registered():
     import mmada_b200.torch_ops as t
     for n in t.OPS:
         assert hasattr(torch.ops.mmada_b200, n)
+    # every launcher the header declares is reachable through a dispatcher-visible op
+    from mmada_b200 import _lib
+    covered = {c for v in t.OPS.values() for c in v}
+    assert set(_lib.SIGNATURES) - covered == {"mmada_abi_version", "mmada_device_arch"}
+    # in-place launchers declare what they mutate
+    schema = str(torch.ops.mmada_b200.t2i_sample_step.default._schema)
+    assert "Tensor(a" in schema and "known" in schema
+    assert "Tensor(a" in str(torch.ops.mmada_b200.gemm_resid_norm.default._schema)
+    assert "Tensor(a" in str(torch.ops.mmada_b200.text_transfer.default._schema)
     with FakeTensorMode():
         a = torch.empty(100, 64, dtype=torch.bfloat16, device="cuda")
         w = torch.empty(256, 64, dtype=torch.bfloat16, device="cuda")

@@ -332,3 +332,22 @@ def test_torch_ops_route_equals_direct_route():
     assert torch.equal(torch.ops.mmada_b200.rmsnorm(x, wt, 1e-5), ops.rmsnorm(x, wt, 1e-5))
     qkv = torch.randn(2 * 150, 3 * 256, device="cuda", generator=g).bfloat16()
     assert torch.equal(torch.ops.mmada_b200.attention(qkv, 2, 150, 2, 128), ops.attention(qkv, 2, 150, 2, 128))
+    # an in-place op through the dispatcher: the sampling step mutates known / input_ids like the direct route
+    B, N, C = 2, 64, 512
+    cond = torch.randn(B * N, C, device="cuda", generator=g)
+    q = torch.empty(B * N, C, device="cuda").exponential_(1, generator=g)
+    u = torch.rand(B, N, device="cuda", generator=g)
+    k1 = torch.full((B, N), 126336, dtype=torch.int64, device="cuda")
+    k2 = k1.clone()
+    t1, t2 = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    r1 = torch.ops.mmada_b200.t2i_sample_step(cond, None, q, u, k1, None, 0, t1, 0.0, 20.0, 0.5, 126336, 126349)
+    r2 = ops.t2i_sample_step(cond, None, q, u, k2, None, 0, t2, 0.0, 20.0, 0.5, 126336, 126349, want_masking=True)
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[2], r2[2]) and torch.equal(k1, k2) and not torch.equal(k1, torch.full_like(k1, 126336))
+    x = torch.randn(300, 512, device="cuda", generator=g)
+    x2 = x.clone()
+    xb, ssq = torch.empty(300, 512, device="cuda", dtype=torch.bfloat16), torch.empty(300, 2, device="cuda")
+    xb2, ssq2 = torch.empty_like(xb), torch.empty_like(ssq)
+    w2 = torch.randn(512, 512, device="cuda", generator=g).bfloat16()
+    torch.ops.mmada_b200.gemm_resid_norm(a, w2, x, xb, ssq)
+    ops.gemm_resid_norm(a, w2, x2, xb2, ssq2)
+    assert torch.equal(x, x2) and torch.equal(xb, xb2) and torch.equal(ssq, ssq2)
