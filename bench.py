@@ -699,6 +699,14 @@ def run_other(args):
     gemm_events, ops.GEMM_EVENTS = ops.GEMM_EVENTS, None
     launches = model.kernel_launches - l0
     clocks = sampler.stop()
+    # host cost of ENQUEUING one step with an empty launch queue (the timed run fills the queue and then blocks on it)
+    torch.cuda.synchronize()
+    ids_1 = idx_h.to(dev).clone()
+    torch.cuda.synchronize()
+    t_h1 = time.perf_counter()
+    run(1, ids_1)
+    host_step_ms = (time.perf_counter() - t_h1) * 1e3
+    torch.cuda.synchronize()
     # e2e: host prompt in, host result out, one whole generation of K-equivalent steps
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -764,8 +772,8 @@ def run_other(args):
                        "parallelism": f"prompt-shard x{world}", "l2": "inputs_exceed_l2 (16 GB of weights streamed per step)"},
             "e2e": {"value": units_per_step * Kr / (ms_e2e / 1e3), "unit": "motions/s" if args.config == "t2m" else "tokens/s",
                     "h2d_bytes_per_step": idx_h.numel() * 8 / Kr, "d2h_bytes_per_step": res_h.numel() * res_h.element_size() / Kr},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms / Kr,
-            "launch_bound": bool(host_ms > 0.9 * ms),
+            "gpu_launches": launches, "host_enqueue_ms_per_step_queue_full": host_ms / Kr,
+            "host_enqueue_ms_per_step_queue_empty": host_step_ms, "launch_bound": bool(host_step_ms > 0.9 * ms / Kr),
             "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "power_w_max", "samples")},
             "roofline": roof, "hbm_kernels": hbm, "cpu_baseline": None}
     print(json.dumps(line), flush=True)

@@ -89,4 +89,4 @@ if __name__ == "__main__":
     tag, lcsv, grep_, arep = sys.argv[1:5]
     launches(tag, lcsv)
     traffic(tag, full(tag, "gemm", grep_))
-    full(tag, "attention_pair", arep)
+    full(tag, "attention_duo", arep)
