@@ -421,12 +421,16 @@ static int dispatch_attention(const void* q, const void* k, const void* v, int64
     }
 }
 
-// attention_duo.cu: persistent, two query tiles per CTA in ping-pong, one thread per query row, head_dim 128
+// attention_duo64.cu (the product's head_dim-128 kernel): persistent, two query tiles per CTA, one thread per query row,
+// the scores of every tile double-buffered in 64-key sub-tiles, one MMA-issuing warp per tile
+int launch_attention_duo64(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                           int Lq, int H, float scale, int poly, cudaStream_t stream);
+#ifdef MMADA_EXPERIMENTS
+// EXPERIMENTS builds only (A/B runs): attention_duo.cu = two query tiles in ping-pong with P over
+// its own 128-key score tile (the product kernel before attention_duo64.cu); attention_quad.cu = CTA pairs with two
+// 256-row query blocks in flight and P through shared memory; attention_pair.cu = round 1's pair kernel
 int launch_attention_duo(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                          int Lq, int H, float scale, int poly, cudaStream_t stream);
-#ifdef MMADA_EXPERIMENTS
-// EXPERIMENTS builds only (A/B runs): attention_quad.cu = CTA pairs with two 256-row query blocks in
-// flight and P through shared memory; attention_pair.cu = round 1's pair kernel
 int launch_attention_quad(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream);
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
@@ -457,12 +461,13 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
             // worth it once the extra items would cost a wave of their own.
             auto main_kernel = [&](int Lq) {
 #ifdef MMADA_EXPERIMENTS
-                // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu (the product's), 2 attention_quad.cu
-                static const int which = experiment_env("MMADA_ATT_KERNEL", 1);
+                // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu, 2 attention_quad.cu, 3 attention_duo64.cu (the product's)
+                static const int which = experiment_env("MMADA_ATT_KERNEL", 3);
+                if (which == 1) return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 if (which == 2) return launch_attention_quad(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 if (which == 0) return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
 #endif
-                return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
+                return launch_attention_duo64(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
             };
             static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
             const int rem = L % 256;

@@ -216,7 +216,10 @@ def test_embed():
                                    (2, 40, 700), (3, 60, 130), (5, 32, 1024),
                                    # head_dim 128, B*H >= 148 and L % 256 <= 128: whole 256-row items on the pair kernel,
                                    # the last rows of every (batch, head) on the single-CTA kernel (two launches)
-                                   (5, 32, 1539), (2, 80, 300), (4, 40, 640)])
+                                   (5, 32, 1539), (2, 80, 300), (4, 40, 640),
+                                   # head_dim 128, 1..8 rows behind the last 256-row item: the mma.sync tail warp of the
+                                   # persistent kernel (one launch); 9 rows: not folded
+                                   (2, 3, 264), (3, 5, 773), (1, 2, 513), (2, 2, 521)])
 def test_attention(hd, B, H, L):
     from mmada_b200 import ops
     d = H * hd
