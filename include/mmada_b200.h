@@ -166,6 +166,13 @@ int mmada_text_transfer(int64_t* x, int64_t ld, int lo, int block, const int64_t
                         const double* conf_override, const int32_t* cnt, int steps, int step, int B,
                         int64_t mask_id, uint8_t* transfer_out, void* stream);
 
+/* ---- training-time forward: masked cross-entropy rows -------------------------------------------
+ * nll[r] = logsumexp(logits[r, 0..V)) - logits[r, labels[r]]  (fp32, row pitch ld elements); 0 where
+ * labels[r] == ignore_index.  One pass over each row.  Replaces F.cross_entropy(..., reduction='none') on
+ * the loss rows of MMadaModelLM.forward_process, models/modeling_mmada.py:240-243,253-256,264-267.        */
+int mmada_cross_entropy_rows_f32(const float* logits, int64_t ld, const int64_t* labels, int64_t ignore_index,
+                                 float* nll_out, int R, int V, void* stream);
+
 /* ---- MAGVIT-v2 token -> pixel path ------------------------------------------------------------
  * Activations are NHWC (channels contiguous).  conv: implicit GEMM on tcgen05, zero padding by TMA
  * out-of-bounds fill; in bf16 [B,H,W,C_in] (C_in % 64 == 0), weight bf16 [C_out][taps][C_in] (taps 9 = 3x3

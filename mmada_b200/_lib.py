@@ -31,6 +31,7 @@ SIGNATURES = {
     "mmada_embed_f32": [_p, _p, _p, _i, _i, _i64, _p],
     "mmada_rmsnorm_bf16": [_p, _p, _p, _p, _i, _i, _f, _p],
     "mmada_gather_rows": [_p, _i64, _p, _p, _i, _i, _p],
+    "mmada_cross_entropy_rows_f32": [_p, _i64, _p, _i64, _p, _i, _i, _p],
     "mmada_rope_inplace_bf16": [_p, _i64, _p, _p, _i, _i, _i, _i, _p],
     "mmada_attention_bf16": [_p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _f, _p],
     "mmada_t2i_sample_step": [_p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i, _p, _i, _i, _i, _f, _f, _f, _f,

@@ -94,7 +94,10 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
                                             seed=seed + k)
             override = None
             if remasking == 'random':
-                override = torch.rand((B, block_length), device=dev).to(torch.float64)
+                # the reference's draw (generate.py:90, modeling_mmada.py:455): (B, L) fp32 uniforms from the device's
+                # global generator — same shape, dtype and order, so a seeded generator reproduces its stream; only the
+                # current block's columns can be selected (the rest is -inf there)
+                override = torch.rand((B, L), device=dev)[:, lo:lo + block_length].to(torch.float64).contiguous()
             tr = ops.text_transfer(x, lo, block_length, x0, conf, cnt, steps, i, mask_id, conf_override=override,
                                    want_transfer=trace is not None)
             if hasattr(model, "kernel_launches"):
@@ -102,7 +105,7 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
             if trace is not None:
                 trace.append(dict(k=k, block=num_block, step=i, x0=x0.view(B, block_length).clone(),
                                   conf=conf.view(B, block_length).clone(), transfer=tr, x=x.clone(),
-                                  logits=logits))
+                                  logits=logits, override=override))
             k += 1
         if eot_token is not None:
             last = lo + block_length - 1

@@ -284,3 +284,60 @@ class MMadaModelLM(LLaDAModelLM):
         return _generate_fn(self, idx, steps=steps, gen_length=max_new_tokens, block_length=block_length,
                                   temperature=temperature, cfg_scale=cfg_scale, remasking=remasking, mask_id=mask_id,
                                   attention_mask=attention_mask, eot_token=eot_token, **kwargs)
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_process(self, input_ids, labels, batch_size_t2i=0, batch_size_lm=0, batch_size_mmu=0, max_seq_length=128,
+                        p_mask_lm=None, p_mask_mmu=None, answer_lengths=None, t2i_masks=None, answer_lengths_lm=None,
+                        return_logits: bool = False):
+        """Forward values of the reference's training step (modeling_mmada.py:213-276): ``(logits, loss_t2i, loss_lm,
+        loss_mmu)`` for a mixed t2i / lm / mmu batch — same arguments, same reductions, same quirks (oracle/training.py
+        lists them), no autograd: this is the evaluation of the losses (validation / logging), the backward pass is out
+        of scope.
+
+        What runs underneath: one transformer forward; ``ln_f`` and the output head only on the token rows a loss reads
+        (t2i positions behind the text prefix whose label is not -100, the masked positions of the lm and mmu rows); one
+        pass of ``mmada_cross_entropy_rows_f32`` over those logits.  The reference's ``attention_bias`` from
+        ``t2i_masks`` is never applied by its attention (Q1) and is not built.  ``logits`` is ``None`` unless
+        ``return_logits`` (the reference returns the full (B, L, V) tensor; its training scripts discard it)."""
+        dev = self.device
+        ids = input_ids.to(dev)
+        lab = labels.to(dev)
+        B, L = ids.shape
+        mask_id = self.config.mask_token_id
+        masked = ids == mask_id                                                               # :246
+        lo_lm, hi_lm = batch_size_t2i, batch_size_t2i + batch_size_lm
+        lo_mmu = (B - batch_size_mmu) if batch_size_mmu > 0 else 0                            # [-0:] is the whole batch (:249)
+        pos = torch.arange(B * L, device=dev, dtype=torch.int64).view(B, L)
+        # loss rows (flattened token-row indices), in the reference's boolean-mask (row-major) order
+        if batch_size_t2i > 0:
+            t2i_sel = torch.zeros_like(masked)
+            t2i_sel[:batch_size_t2i, max_seq_length + 1:] = lab[:batch_size_t2i, max_seq_length + 1:] != -100
+            rows_t2i = pos[t2i_sel]
+        else:
+            rows_t2i = pos[:0, 0]
+        masked_lm = masked[lo_lm:hi_lm]
+        masked_mmu = masked[lo_mmu:]
+        rows_lm = pos[lo_lm:hi_lm][masked_lm]
+        rows_mmu = pos[lo_mmu:][masked_mmu]
+        n_t2i, n_lm = rows_t2i.numel(), rows_lm.numel()
+        rows = torch.cat([rows_t2i, rows_lm, rows_mmu])
+        nll = torch.zeros((0,), dtype=torch.float32, device=dev)
+        if rows.numel() > 0:
+            lg = self.logits_rows(ids, rows.to(torch.int32).contiguous())                     # [n_rows, V] fp32
+            nll = ops.cross_entropy_rows(lg, lab.view(-1)[rows], -100)
+            self.kernel_launches += 1
+            del lg
+        # ---- the reference's reductions, on the per-row losses
+        if batch_size_t2i == 0:
+            loss_t2i = torch.tensor(0.0, device=dev)                                          # :237
+        else:
+            loss_t2i = nll[:n_t2i].sum() / n_t2i if n_t2i > 0 else torch.tensor(float("nan"), device=dev)   # mean over targets
+        n_rows_lm = float(max(min(hi_lm, B) - lo_lm, 0))                                      # logits[lm].shape[0]
+        ce_lm = nll[n_t2i:n_t2i + n_lm] / p_mask_lm.to(dev)[masked_lm]                        # :253-256
+        loss_lm = ce_lm.sum() / torch.tensor(n_rows_lm * L, device=dev)                       # :258 (a scalar ...)
+        loss_lm = torch.sum(loss_lm / answer_lengths_lm.to(dev)[masked_lm]) / torch.tensor(n_rows_lm, device=dev)   # :262
+        ce_mmu = nll[n_t2i + n_lm:] / p_mask_mmu.to(dev)[masked_mmu]                          # :264-267
+        loss_mmu = torch.sum(ce_mmu / answer_lengths.to(dev)[masked_mmu]) / float(B - lo_mmu)  # :268
+        logits = self.forward(ids).logits if return_logits else None
+        return logits, loss_t2i, loss_lm, loss_mmu

@@ -203,6 +203,18 @@ def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cross_entropy_rows(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """Per-row ``F.cross_entropy(logits, labels, ignore_index=..., reduction='none')`` (fp32 [R, V] rows, int64 labels):
+    logsumexp(row) - row[label], 0 where the label is ``ignore_index`` (modeling_mmada.py:240-243,253-256,264-267)."""
+    _chk(logits, torch.float32, "logits"); _chk(labels, torch.int64, "labels")
+    assert logits.dim() == 2 and logits.stride(1) == 1 and labels.numel() == logits.shape[0]
+    labels = labels.contiguous().view(-1)
+    out = torch.empty((logits.shape[0],), dtype=torch.float32, device=logits.device)
+    _call((logits, labels, out,), "mmada_cross_entropy_rows_f32", logits.data_ptr(), logits.stride(0), labels.data_ptr(),
+          int(ignore_index), out.data_ptr(), logits.shape[0], logits.shape[1])
+    return out
+
+
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, rows: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(x, torch.float32, "x"); _chk(weight, torch.float32, "weight")

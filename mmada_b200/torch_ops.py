@@ -156,6 +156,17 @@ def _(x, rows):
     return x.new_empty((rows.numel(), x.shape[1]))
 
 
+@custom_op("mmada_b200::cross_entropy_rows", mutates_args=(), device_types="cuda")
+def cross_entropy_rows(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """F.cross_entropy(..., reduction='none') per row (modeling_mmada.py:240-267) — mmada_cross_entropy_rows_f32."""
+    return ops.cross_entropy_rows(logits, labels, ignore_index)
+
+
+@cross_entropy_rows.register_fake
+def _(logits, labels, ignore_index=-100):
+    return logits.new_empty((logits.shape[0],), dtype=torch.float32)
+
+
 @custom_op("mmada_b200::rope_inplace", mutates_args=("qkv",), device_types="cuda")
 def rope_inplace(qkv: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, d_model: int, head_dim: int, seq_len: int) -> None:
     """RotaryEmbedding (modeling_llada.py:402-428) in place on the q and k thirds — mmada_rope_inplace_bf16."""
@@ -390,7 +401,7 @@ OPS = {
     "conv_nhwc": ("mmada_conv_nhwc_bf16",), "gemm_resid_norm": ("mmada_gemm_resid_norm_f32",),
     "gemm_swiglu_rownorm": ("mmada_gemm_swiglu_rownorm_bf16",), "gemm_qkv_rope_rownorm": ("mmada_gemm_qkv_rope_rownorm_bf16",),
     "embed": ("mmada_embed_f32",), "embed_norm": ("mmada_embed_norm_f32",), "gather_rows": ("mmada_gather_rows",),
-    "rope_inplace": ("mmada_rope_inplace_bf16",),
+    "rope_inplace": ("mmada_rope_inplace_bf16",), "cross_entropy_rows": ("mmada_cross_entropy_rows_f32",),
     "t2i_sample_step": ("mmada_t2i_sample_step", "mmada_t2i_sample_step_compact"),
     "compact_masked_rows": ("mmada_compact_masked_rows",), "text_sample_rows": ("mmada_text_sample_rows",),
     "block_mask_count": ("mmada_block_mask_count",), "text_transfer": ("mmada_text_transfer",),

@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-from . import denoise, llada, magvit, ref_bootstrap as rb, weights as W
+from . import denoise, llada, magvit, ref_bootstrap as rb, training, weights as W
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -275,6 +275,26 @@ def logits_case(name, cfg, B, L, wseed, seed):
           absmax=ref.abs().max(), std=ref.std(), meta=np.array([B, L, wseed, seed]))
 
 
+def forward_process_case(name, cfg, B_t2i, B_lm, B_mmu, L, max_seq_length, wseed, seed):
+    """MMadaModelLM.forward_process (modeling_mmada.py:213-276, forward values): the real method against
+    oracle/training.py on a synthetic mixed t2i / lm / mmu batch."""
+    print(f"[forward_process] {name}")
+    sd = W.make_llada_weights(cfg, wseed)
+    model = rb.build_model(cfg, sd)
+    bt = training.make_batch(B_t2i, B_lm, B_mmu, L, max_seq_length, seed, cfg["mask_token_id"])
+    kw = dict(batch_size_t2i=B_t2i, batch_size_lm=B_lm, batch_size_mmu=B_mmu, max_seq_length=max_seq_length,
+              p_mask_lm=bt["p_mask_lm"], p_mask_mmu=bt["p_mask_mmu"], answer_lengths=bt["answer_lengths"],
+              t2i_masks=bt["t2i_masks"], answer_lengths_lm=bt["answer_lengths_lm"])
+    with torch.no_grad():
+        ref = model.forward_process(bt["input_ids"].clone(), bt["labels"].clone(), **kw)
+    mine = training.forward_process(lambda ids: llada.forward_logits(ids, sd, cfg), bt["input_ids"].clone(),
+                                    bt["labels"].clone(), mask_token_id=cfg["mask_token_id"], **kw)
+    for a, b, what in zip(ref, mine, ("logits", "loss_t2i", "loss_lm", "loss_mmu")):
+        assert torch.equal(a, b), f"restatement != reference (forward_process {what})"
+    _save(name, loss_t2i=ref[1], loss_lm=ref[2], loss_mmu=ref[3], logits_sub=ref[0][:, ::5, ::997],
+          meta=np.array([B_t2i, B_lm, B_mmu, L, max_seq_length, wseed, seed]))
+
+
 def prompting_case():
     """training/prompting_utils.py (the real class, stub tokenizer) against oracle/prompting.py; stores ragged inputs and
     the reference's outputs."""
@@ -367,6 +387,7 @@ def main():
     magvit_encoder_case()
     motion_case()
     prompting_case()
+    forward_process_case("forward_process_tiny", W.TINY, B_t2i=2, B_lm=2, B_mmu=2, L=96, max_seq_length=31, wseed=0, seed=41)
     logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
     logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
     t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)

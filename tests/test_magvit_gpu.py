@@ -100,6 +100,13 @@ def test_decode_code_vs_reference_golden(golden):
     u8 = vq.decode_code_uint8(idx)
     exp = (torch.clamp((pix + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).cpu().numpy().astype(np.uint8)
     assert np.array_equal(u8.cpu().numpy(), exp)
+    # the post-processed image (inference_t2i.py:123-125) against the reference's own fp32 pixels, in uint8 levels: the
+    # reference keeps MAGVIT in fp32, this decoder feeds bf16 conv operands
+    ref_u8 = (torch.clamp((ref + 1.0) / 2.0, 0.0, 1.0) * 255.0).permute(0, 2, 3, 1).numpy().astype(np.uint8)
+    d_u8 = np.abs(u8.cpu().numpy()[:, ::2, ::2, :].astype(np.int32) - ref_u8.astype(np.int32))
+    print(f"decode_code uint8 vs reference fp32 image: max {int(d_u8.max())} levels, mean {d_u8.mean():.3f}, "
+          f"identical {float((d_u8 == 0).mean()):.3f}, within 1 level {float((d_u8 <= 1).mean()):.3f}")
+    assert int(d_u8.max()) <= 6 and float(d_u8.mean()) < 1.0
     with pytest.raises(Exception, match="no encoder weights"):
         vq.get_code(pix)
 

@@ -170,3 +170,62 @@ def test_t2i_stepwise_yields_images():
     import numpy as np
     last = np.asarray(frames[-1][0])
     assert np.array_equal(last, vq.decode_code_uint8(out[:1].clamp(0, 8191))[0].cpu().numpy())
+
+
+def test_cross_entropy_rows_vs_torch():
+    """mmada_cross_entropy_rows_f32 against F.cross_entropy(reduction='none') on the same fp32 logits (tolerance 2e-6
+    relative: order of the fp32 sum of exponentials), ignore_index rows, a non-multiple-of-4 vocabulary, strided rows."""
+    import torch.nn.functional as F
+    from mmada_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for R, V in ((37, 134656), (5, 1003), (64, 8192)):
+        lg = (torch.randn(R, V, generator=g) * 4).cuda()
+        lab = torch.randint(0, V, (R,), generator=g).cuda()
+        lab[::7] = -100
+        ref = F.cross_entropy(lg.double(), lab, ignore_index=-100, reduction="none").float()
+        out = ops.cross_entropy_rows(lg, lab, -100)
+        assert torch.equal(out[::7], torch.zeros_like(out[::7]))
+        torch.testing.assert_close(out, ref, rtol=2e-6, atol=2e-6)
+    wide = (torch.randn(9, 4096 + 64, generator=g)).cuda()
+    lab = torch.randint(0, 4096, (9,), generator=g).cuda()
+    torch.testing.assert_close(ops.cross_entropy_rows(wide[:, :4096], lab), F.cross_entropy(wide[:, :4096], lab, reduction="none"),
+                               rtol=2e-6, atol=2e-6)
+
+
+def test_forward_process_matches_reference_golden(golden):
+    """MMadaModelLM.forward_process (modeling_mmada.py:213-276, forward values) on a mixed t2i / lm / mmu batch:
+    (a) the loss reductions replayed by the CPU oracle on the CUDA path's own full logits — 1e-5 relative (fp32
+    summation order); (b) against the REAL reference's fp32 losses from tests/golden — 2e-2 relative (bf16 weights and
+    activations; north_star's logit tolerance)."""
+    from mmada_b200 import MMadaConfig, MMadaModelLM
+    from oracle import training, weights as W
+    gd = golden("forward_process_tiny")
+    B_t2i, B_lm, B_mmu, L, msl, wseed, seed = (int(v) for v in gd["meta"])
+    m = MMadaModelLM(MMadaConfig.from_dict(W.TINY)).load_state_dict(W.make_llada_weights(W.TINY, wseed))
+    bt = training.make_batch(B_t2i, B_lm, B_mmu, L, msl, seed, W.TINY["mask_token_id"])
+    kw = dict(batch_size_t2i=B_t2i, batch_size_lm=B_lm, batch_size_mmu=B_mmu, max_seq_length=msl, p_mask_lm=bt["p_mask_lm"],
+              p_mask_mmu=bt["p_mask_mmu"], answer_lengths=bt["answer_lengths"], t2i_masks=bt["t2i_masks"],
+              answer_lengths_lm=bt["answer_lengths_lm"])
+    logits, l_t2i, l_lm, l_mmu = m.forward_process(bt["input_ids"].cuda(), bt["labels"].cuda(), return_logits=True, **kw)
+    assert logits.shape == (B_t2i + B_lm + B_mmu, L, W.TINY["vocab_size"])
+    none_logits = m.forward_process(bt["input_ids"].cuda(), bt["labels"].cuda(), **kw)
+    assert none_logits[0] is None and all(torch.equal(a, b) for a, b in zip(none_logits[1:], (l_t2i, l_lm, l_mmu)))
+    full = logits.cpu()
+    _, o_t2i, o_lm, o_mmu = training.forward_process(lambda ids: full, bt["input_ids"], bt["labels"],
+                                                     mask_token_id=W.TINY["mask_token_id"], **kw)
+    for mine, orc, ref, name in ((l_t2i, o_t2i, gd["loss_t2i"], "t2i"), (l_lm, o_lm, gd["loss_lm"], "lm"),
+                                 (l_mmu, o_mmu, gd["loss_mmu"], "mmu")):
+        a, b, c = float(mine), float(orc), float(ref)
+        print(f"forward_process loss_{name}: cuda {a:.6f}  oracle on the same logits {b:.6f}  reference fp32 {c:.6f}")
+        assert abs(a - b) <= 1e-5 * abs(b)
+        assert abs(a - c) <= 2e-2 * abs(c)
+    sub = torch.from_numpy(gd["logits_sub"])
+    err = float((full[:, ::5, ::997] - sub).abs().max() / sub.abs().max())
+    assert err <= 2e-2
+    # batch_size_mmu = 0: the reference's [-0:] slices take the whole batch (kept)
+    z = dict(kw, batch_size_mmu=0, p_mask_mmu=torch.full((B_t2i + B_lm + B_mmu, L), 0.5),
+             answer_lengths=torch.full((B_t2i + B_lm + B_mmu, L), 7))
+    _, _, _, q_mmu = m.forward_process(bt["input_ids"].cuda(), bt["labels"].cuda(), **z)
+    _, _, _, qo_mmu = training.forward_process(lambda ids: full, bt["input_ids"], bt["labels"],
+                                               mask_token_id=W.TINY["mask_token_id"], **z)
+    assert abs(float(q_mmu) - float(qo_mmu)) <= 1e-5 * abs(float(qo_mmu))

@@ -127,3 +127,20 @@ def test_motion_decoder(golden):
         pose = motion.forward_decoder(torch.from_numpy(gd["ids"]), sd)
     assert pose.shape == (1, 49 * 4, 263)
     assert np.array_equal(pose.numpy(), gd["pose"])
+
+
+def test_forward_process_oracle_reproduces_reference_losses(golden):
+    """oracle/training.py on the synthetic mixed batch: the losses stored from the REAL reference's forward_process,
+    bit for bit (same torch ops on the same fp32 logits)."""
+    from oracle import llada, training, weights as W
+    gd = golden("forward_process_tiny")
+    B_t2i, B_lm, B_mmu, L, msl, wseed, seed = (int(v) for v in gd["meta"])
+    sd = W.make_llada_weights(W.TINY, wseed)
+    bt = training.make_batch(B_t2i, B_lm, B_mmu, L, msl, seed, W.TINY["mask_token_id"])
+    lg, l_t2i, l_lm, l_mmu = training.forward_process(
+        lambda ids: llada.forward_logits(ids, sd, W.TINY), bt["input_ids"], bt["labels"], batch_size_t2i=B_t2i,
+        batch_size_lm=B_lm, batch_size_mmu=B_mmu, max_seq_length=msl, p_mask_lm=bt["p_mask_lm"], p_mask_mmu=bt["p_mask_mmu"],
+        answer_lengths=bt["answer_lengths"], t2i_masks=bt["t2i_masks"], answer_lengths_lm=bt["answer_lengths_lm"],
+        mask_token_id=W.TINY["mask_token_id"])
+    assert np.array_equal(lg[:, ::5, ::997].numpy(), gd["logits_sub"])
+    assert float(l_t2i) == float(gd["loss_t2i"]) and float(l_lm) == float(gd["loss_lm"]) and float(l_mmu) == float(gd["loss_mmu"])

@@ -136,3 +136,40 @@ def test_mmu_generate_equals_generate_and_fast_exit(golden):
         mmada_b200.generate(m, prompt, steps=steps, gen_length=gen, block_length=block, remasking="nope")
     with pytest.raises(AssertionError):
         mmada_b200.generate(m, prompt, steps=steps, gen_length=gen, block_length=7)
+
+
+def test_generate_random_remasking_matches_oracle_replay(golden):
+    """remasking='random' (generate.py:89-90): the confidences are (B, L) fp32 uniforms from the device generator, drawn
+    exactly like the reference draws them; decisions replayed on the CPU with the same draws."""
+    import mmada_b200
+    from oracle import denoise, weights as W
+    gd = golden("text_t0")
+    B, Lp, gen, block, steps, wseed, seed = (int(v) for v in gd["meta"])
+    m = _model(W.TINY, wseed)
+    prompt = torch.from_numpy(gd["prompt"])
+    L = Lp + gen
+    torch.cuda.manual_seed(1234)
+    trace = []
+    x = mmada_b200.generate(m, prompt.cuda(), steps=steps, gen_length=gen, block_length=block, temperature=0.0,
+                            remasking="random", trace=trace)
+    # the same stream again: one (B, L) draw per forward, in order
+    torch.cuda.manual_seed(1234)
+    xo = torch.full((B, L), 126336, dtype=torch.long)
+    xo[:, :Lp] = prompt
+    spb = steps // (gen // block)
+    for t in trace:
+        nb, i = t["block"], t["step"]
+        lo = Lp + nb * block
+        r = torch.rand((B, L), device="cuda").cpu()
+        assert torch.equal(t["override"].cpu(), r[:, lo:lo + block].double())
+        if i == 0:
+            ntt = denoise.get_num_transfer_tokens(xo[:, lo:lo + block] == 126336, spb)
+        x0, _ = denoise.text_sample_rows(t["logits"].cpu()[:B * block], 0.0, None)
+        assert torch.equal(t["x0"].cpu().reshape(-1), x0)
+        masked = xo[:, lo:lo + block] == 126336
+        conf = torch.where(masked, r[:, lo:lo + block], torch.tensor(-np.inf))
+        for j in range(B):
+            _, sel = torch.topk(conf[j], k=int(ntt[j, i]))
+            xo[j, lo + sel] = x0.view(B, block)[j, sel]
+        assert torch.equal(t["x"].cpu(), xo), (nb, i)
+    assert torch.equal(x.cpu(), xo) and int((x == 126336).sum()) == 0
