@@ -105,7 +105,7 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
             if trace is not None:
                 trace.append(dict(k=k, block=num_block, step=i, x0=x0.view(B, block_length).clone(),
                                   conf=conf.view(B, block_length).clone(), transfer=tr, x=x.clone(),
-                                  logits=logits, override=override))
+                                  logits=logits.clone(), override=override))     # (a graph replay reuses the buffer)
             k += 1
         if eot_token is not None:
             last = lo + block_length - 1

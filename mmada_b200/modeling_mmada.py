@@ -324,7 +324,7 @@ class MMadaModelLM(LLaDAModelLM):
         rows = torch.cat([rows_t2i, rows_lm, rows_mmu])
         nll = torch.zeros((0,), dtype=torch.float32, device=dev)
         if rows.numel() > 0:
-            lg = self.logits_rows(ids, rows.to(torch.int32).contiguous())                     # [n_rows, V] fp32
+            lg = self._logits_rows(ids, rows.to(torch.int32).contiguous())                    # [n_rows, V] fp32 (no graph: the row count changes per batch)
             nll = ops.cross_entropy_rows(lg, lab.view(-1)[rows], -100)
             self.kernel_launches += 1
             del lg

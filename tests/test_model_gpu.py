@@ -229,3 +229,33 @@ def test_forward_process_matches_reference_golden(golden):
     _, _, _, qo_mmu = training.forward_process(lambda ids: full, bt["input_ids"], bt["labels"],
                                                mask_token_id=W.TINY["mask_token_id"], **z)
     assert abs(float(q_mmu) - float(qo_mmu)) <= 1e-5 * abs(float(qo_mmu))
+
+
+def test_logits_rows_cuda_graph_replay_is_bit_identical():
+    """Small workloads replay logits_rows from a CUDA graph (one per shape): same bits as the eager launches, for new
+    ids / row lists of the same shape, after a flag change (its own graph) and after reloading weights (graphs dropped)."""
+    from mmada_b200 import MMadaConfig, MMadaModelLM
+    from oracle import weights as W
+    m = MMadaModelLM(MMadaConfig.from_dict(W.TINY)).load_state_dict(W.make_llada_weights(W.TINY, 0))
+    g = torch.Generator().manual_seed(0)
+    B, L = 2, 70
+    outs = []
+    for rep in range(3):
+        ids = torch.randint(0, 126000, (B, L), generator=g).cuda()
+        rows = torch.randperm(B * L, generator=g)[:40].sort().values.to(torch.int32).cuda()
+        m.graph_max_token_rows = 0
+        eager = m.logits_rows(ids, rows, 100, 100 + 512)
+        m.graph_max_token_rows = 8192
+        n0 = m.kernel_launches
+        graphed = m.logits_rows(ids, rows, 100, 100 + 512)
+        assert torch.equal(eager, graphed) and m.kernel_launches > n0
+        outs.append(graphed)
+    assert len(m._graphs) == 1 and not torch.equal(outs[0], outs[1])             # one shape, one graph; results are copies
+    m.restrict_last_block = False
+    assert torch.equal(m.logits_rows(ids, rows, 100, 100 + 512), eager) and len(m._graphs) == 2
+    m.load_state_dict(W.make_llada_weights(W.TINY, 1))
+    assert len(m._graphs) == 0
+    m.graph_max_token_rows = 0
+    other = m.logits_rows(ids, rows, 100, 100 + 512)
+    m.graph_max_token_rows = 8192
+    assert torch.equal(m.logits_rows(ids, rows, 100, 100 + 512), other) and not torch.equal(other, eager)
