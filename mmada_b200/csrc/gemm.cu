@@ -49,6 +49,7 @@ struct GemmParams {
     int group_m;                             // rasterisation: tiles walk group_m m-tiles before the next n-tile
     int serpentine;                          // odd groups sweep the n-tiles backwards: the B bands the previous group read
                                              // last are still in L2 when the next group starts
+    int group_by_n;                          // 1: the group is group_m N-tiles (a band of B stays in L2) and the m-tiles sweep
     // RMSNorm folded into the GEMMs around it (models/modeling_llada.py:315-329).  Producer (EPI_RESID_NORM_F32):
     // besides x (fp32) the epilogue writes bf16(x) = the next GEMM's A operand and, per n-tile, the row's sum of
     // squares of the 256 new values.  Consumer (row_ssq != nullptr): accumulator rows are scaled by
@@ -74,8 +75,19 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGING_OFF + STAGING_BYTES + 1024 /*align*/;
 };
 
-__device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int GROUP_M, int serpentine, int& mt,
-                                            int& nt) {
+__device__ __forceinline__ void tile_coords(int idx, int num_m_tiles, int num_n_tiles, int GROUP_M, int serpentine,
+                                            int by_n, int& mt, int& nt) {
+    if (by_n) {
+        const int per_group = GROUP_M * num_m_tiles;
+        const int g = idx / per_group;
+        const int first_n = g * GROUP_M;
+        const int gsize = min(GROUP_M, num_n_tiles - first_n);
+        const int r = idx - g * per_group;
+        nt = first_n + r % gsize;
+        mt = r / gsize;
+        if (serpentine && (g & 1)) mt = num_m_tiles - 1 - mt;
+        return;
+    }
     const int per_group = GROUP_M * num_n_tiles;
     const int g = idx / per_group;
     const int first_m = g * GROUP_M;
@@ -267,7 +279,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int mt, nt;
-            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, p.serpentine, mt, nt);
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, p.serpentine, p.group_by_n, mt, nt);
             const int m0 = mt * (BM * CG) + (int)cta_rank * BM;
             const int n0 = nt * BN + (int)cta_rank * Cfg::LOAD_N;
             // convolution: the 128 rows are 128 consecutive NHWC pixels = a BW x BH box of one image
@@ -351,7 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int mt, nt;
-            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, p.serpentine, mt, nt);
+            tile_coords(t, p.num_m_tiles, p.num_n_tiles, p.group_m, p.serpentine, p.group_by_n, mt, nt);
             const int row = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32 + lane;
             uint8_t* stage = smem + Cfg::STAGING_OFF + (warp - 2) * (32 * 144);
             const int row0 = mt * (BM * CG) + (int)cta_rank * BM + quarter * 32;       // first row of this warp
@@ -646,9 +658,20 @@ static void set_tuning(GemmParams& p) {
     // default: 16 m-tiles per group (the A band, 16 x 256 rows x K, stays in L2 while the n-tiles sweep past it);
     // for long K the band outgrows L2 and a squarer wave re-reads less (K = 12288: 3.7 GB at 8 against 4.1 GB at 16;
     // K = 4096: 2.5 GB at 16 against 3.5 GB at 8)
-    p.group_m = group_m ? group_m : (p.K >= 8192 ? 8 : 16);
-    p.hint_a = ha; p.hint_b = hb;
+    // round 2 (profiles/r02c_gemm_by_n_probe.txt): grouping the N-tiles instead (a band of B = weights stays in L2 while
+    // the m-tiles sweep, odd groups backwards) re-reads less for every block shape: the operand that is streamed once
+    // per group is then read ceil(Nt / g) times instead of ceil(Mt / g) — ff_out (K = 12288) 3.94 -> 3.56 GB at g = 8,
+    // q|k|v 1.70 -> 1.57 at g = 12, attn_out 1.39 -> 1.25 at g = 8, gate|up 2.70 -> 2.58 at g = 16
+    const int by_n = experiment_env("MMADA_GEMM_BY_N", -1);
     p.serpentine = experiment_env("MMADA_GEMM_SERPENTINE", 1);
+    if (by_n != 0) {
+        p.group_by_n = 1;
+        p.group_m = group_m ? group_m : (p.K >= 8192 || p.N <= 4096 ? 8 : (p.N <= 12288 ? 12 : 16));
+    } else {
+        p.group_by_n = 0;
+        p.group_m = group_m ? group_m : (p.K >= 8192 ? 8 : 16);
+    }
+    p.hint_a = ha; p.hint_b = hb;
 }
 
 // row_ssq / ssq_tiles / norm_dim / eps: folded RMSNorm on the consumer side (SwiGLU epilogue); xb / ld_xb / ssq_out:
