@@ -455,10 +455,10 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
     cudaStream_t s = (cudaStream_t)stream;
     if (head_dim == 128) {
         if (L > 128) {
-            // The persistent kernel walks items of 256 query rows.  When the last item of every (batch, head) would hold at
-            // most one 128-row tile (L = 1539: 3 rows), those rows go to the single-CTA kernel instead (one CTA per
-            // (batch, head), a second launch on the same stream) and the persistent kernel walks whole items only:
-            // worth it once the extra items would cost a wave of their own.
+            // The persistent kernel walks items of 256 query rows; a last item with at most one 128-row tile (L = 1539: 3 rows)
+            // runs with one slot.  With attention_duo64.cu that costs less than handing those rows to the single-CTA kernel
+            // in a second launch, which re-reads all of K and V from HBM (0.605 against 0.629 ms at config 2, 29.1 against
+            // 29.9 ms per step): the split below is kept for A/B runs of the EXPERIMENTS build only.
             auto main_kernel = [&](int Lq) {
 #ifdef MMADA_EXPERIMENTS
                 // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu, 2 attention_quad.cu, 3 attention_duo64.cu (the product's)
@@ -469,7 +469,7 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
 #endif
                 return launch_attention_duo64(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
             };
-            static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 1);
+            static const int split_tail = experiment_env("MMADA_ATT_SPLIT_TAIL", 0);
             const int rem = L % 256;
             if (split_tail && L > 256 && rem > 0 && rem <= 128 && B * H >= num_sms()) {
                 const int st = main_kernel(L - rem);

@@ -333,6 +333,19 @@ attention_duo64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             int b, h, q0, nqt;
             item_coords(n, b, h, q0, nqt);
             if (s >= nqt) continue;
+            if (q0 + s * 128 + quarter * 32 >= p.Lq) {
+                // none of this warp's 32 query rows exists (the last item of a sequence: L = 1539 leaves 3 rows): keep the
+                // protocol going and do no work.  Their P rows stay whatever the buffer holds — rows of an MMA are
+                // independent and these rows of O are never stored.
+                for (int u = 0; u < T2; ++u, ++c) {
+                    mbar_wait_nocall(bar(B_SFULL + 2 * s + (c & 1)), (c >> 1) & 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_PFULL + 2 * s + (c & 1)));
+                }
+                mbar_wait_nocall(bar(B_OFULL + s), it & 1);
+                ++it;
+                continue;
+            }
             float m_used = -INFINITY, l_sum = 0.f;
             for (int u = 0; u < T2; ++u, ++c) {
                 const int buf = c & 1;
