@@ -347,6 +347,80 @@ attention_duo64_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 continue;
             }
             float m_used = -INFINITY, l_sum = 0.f;
+            if (q0 + s * 128 + quarter * 32 + 8 >= p.Lq) {
+                // ---- at most 8 of this warp's query rows exist (the last item of a sequence: L = 1539 leaves 3).  A thread
+                // per row would spend a full warp's exponentials on them; here FOUR threads share a row (tcgen05.ld.16x256b:
+                // thread t holds row t / 4, key columns 8 i + 2 (t % 4) + {0, 1}; P goes back with st.16x128b, whose
+                // layout is exactly that of the packed pairs): 16 exponentials per thread and sub-tile instead of 64.  Exact
+                // row maximum (two shuffles), lazy rescale as everywhere else; rows 8-31 of the warp are never stored.
+                const int c4 = lane & 3;
+                float lpart = 0.f;                       // this thread's share of its row's sum
+                for (int u = 0; u < T2; ++u, ++c) {
+                    const int buf = c & 1;
+                    const uint32_t t_s = t_s0 + 64 * buf;
+                    mbar_wait_nocall(bar(B_SFULL + 2 * s + buf), (c >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld_16x256b_x8(t_s, v);
+                    tmem_ld_wait();
+                    const int nk = (u == T2 - 1) ? tail : SUB;
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = 8 * i + 2 * c4;
+                        if (col < nk) mx = fmaxf(mx, __uint_as_float(v[4 * i]));
+                        if (col + 1 < nk) mx = fmaxf(mx, __uint_as_float(v[4 * i + 1]));
+                    }
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    const float m_new = fmaxf(m_used, mx);
+                    if (u == 0) {
+                        m_used = m_new;
+                    } else {
+                        const bool grow = (m_new - m_used) * sl2 > 8.0f;
+                        if (__any_sync(0xffffffffu, grow)) {
+                            // O_s quiescent: see the thread-per-row path below
+                            mbar_wait_nocall(bar(B_PVDONE + s), (c - 1) & 1);
+                            tc_fence_after();
+                            const float alpha = grow ? ex2_mufu((m_used - m_new) * sl2) : 1.0f;
+                            if (grow) m_used = m_new;
+                            lpart *= alpha;
+                            float alpha_row = __shfl_sync(0xffffffffu, alpha, (4 * lane) & 31);    // lane r owns lane r of O
+                            if (lane >= 8) alpha_row = 1.0f;
+#pragma unroll 1
+                            for (int cc = 0; cc < HD / 16; ++cc) {
+                                uint32_t ov[16];
+                                tmem_ld_32x32b_x16(t_o + cc * 16, ov);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha_row);
+                                tmem_st_32x32b_x16(t_o + cc * 16, ov);
+                            }
+                            tmem_st_wait();
+                        }
+                    }
+                    const float mb = m_used * sl2;
+                    uint32_t pw[16];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int col = 8 * i + 2 * c4;
+                        const float e0 = col < nk ? ex2_mufu(__uint_as_float(v[4 * i]) * sl2 - mb) : 0.f;
+                        const float e1 = col + 1 < nk ? ex2_mufu(__uint_as_float(v[4 * i + 1]) * sl2 - mb) : 0.f;
+                        lpart += e0 + e1;
+                        pw[2 * i] = pack_bf16(e0, e1);
+                        pw[2 * i + 1] = 0u;                  // rows 8-15
+                    }
+                    tmem_st_16x128b_x8(t_s, pw);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_PFULL + 2 * s + buf));
+                }
+                lpart += __shfl_xor_sync(0xffffffffu, lpart, 1);
+                lpart += __shfl_xor_sync(0xffffffffu, lpart, 2);
+                l_sum = __shfl_sync(0xffffffffu, lpart, (4 * lane) & 31);               // back to one thread per row
+                if (lane >= 8) l_sum = 1.0f;
+            } else
             for (int u = 0; u < T2; ++u, ++c) {
                 const int buf = c & 1;
                 const uint32_t t_s = t_s0 + 64 * buf;   // scores; probabilities (bf16 pairs) over their first 32 columns
