@@ -214,12 +214,15 @@ def test_embed():
 @pytest.mark.parametrize("B,H,L", [(1, 2, 128), (2, 3, 387), (2, 2, 1539), (1, 1, 100), (1, 2, 256), (1, 1, 257),
                                    # more work items than CTA pairs: the persistent path (buffer reuse, phase flips)
                                    (2, 40, 700), (3, 60, 130), (5, 32, 1024),
-                                   # head_dim 128, B*H >= 148 and L % 256 <= 128: whole 256-row items on the pair kernel,
-                                   # the last rows of every (batch, head) on the single-CTA kernel (two launches)
+                                   # head_dim 128, B*H >= 148 and L % 256 <= 128: more items than CTAs, one-slot last items
                                    (5, 32, 1539), (2, 80, 300), (4, 40, 640),
-                                   # head_dim 128, 1..8 rows behind the last 256-row item: the mma.sync tail warp of the
-                                   # persistent kernel (one launch); 9 rows: not folded
-                                   (2, 3, 264), (3, 5, 773), (1, 2, 513), (2, 2, 521)])
+                                   # head_dim 128, 1..8 rows behind the last 256-row item: a one-slot item whose first
+                                   # warp shares every row between four threads; 9 rows: the thread-per-row path
+                                   (2, 3, 264), (3, 5, 773), (1, 2, 513), (2, 2, 521),
+                                   # boundaries: one key, one sub-tile +- 1, one tile +- 1, one item +- 1, 33 rows in the
+                                   # second slot, a last key sub-tile of 1 / 16 / 17 / 63 keys
+                                   (1, 1, 1), (1, 2, 63), (1, 1, 65), (2, 1, 127), (1, 2, 129), (1, 1, 255), (1, 2, 385),
+                                   (1, 1, 417), (1, 2, 272), (1, 1, 273), (1, 1, 319)])
 def test_attention(hd, B, H, L):
     from mmada_b200 import ops
     d = H * hd
@@ -354,3 +357,16 @@ def test_torch_ops_route_equals_direct_route():
     torch.ops.mmada_b200.gemm_resid_norm(a, w2, x, xb, ssq)
     ops.gemm_resid_norm(a, w2, x2, xb2, ssq2)
     assert torch.equal(x, x2) and torch.equal(xb, xb2) and torch.equal(ssq, ssq2)
+
+
+def test_attention_rejects_bad_arguments():
+    """The C entry point returns an error status (raised by the host wrapper) instead of launching: unsupported head
+    size, misaligned pointers / pitches, empty problem."""
+    from mmada_b200 import ops
+    from mmada_b200._lib import MMadaKernelError
+    qkv = torch.zeros(64, 3 * 96, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises((MMadaKernelError, AssertionError, ValueError)):
+        ops.attention(qkv, 1, 64, 1, 96)                         # head_dim 96
+    ok = torch.zeros(64, 3 * 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises((MMadaKernelError, AssertionError, ValueError)):
+        ops.attention(ok, 1, 0, 1, 128)                          # L = 0

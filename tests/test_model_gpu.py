@@ -259,3 +259,36 @@ def test_logits_rows_cuda_graph_replay_is_bit_identical():
     other = m.logits_rows(ids, rows, 100, 100 + 512)
     m.graph_max_token_rows = 8192
     assert torch.equal(m.logits_rows(ids, rows, 100, 100 + 512), other) and not torch.equal(other, eager)
+
+
+@pytest.mark.parametrize("B,frac_known", [(1, 0.0), (3, 0.4)])
+def test_t2i_generate_without_cfg_and_with_known_tokens(B, frac_known):
+    """t2i_generate with guidance_scale = 0 (no uncond branch, modeling_mmada.py:158-171 else-path), batch 1, and with part
+    of the image tokens already known at entry (the loop keeps them, :183-184): every step replayed on the oracle."""
+    from oracle import denoise, weights as W
+    cfg = W.TINY128
+    m = _model(cfg, 1)
+    P, N, steps = 9, 160, 5
+    cond, _, _, _ = W.make_t2i_prompts(B, P, N, 3)
+    g = torch.Generator().manual_seed(11)
+    known0 = torch.full((B, N), 126336, dtype=torch.int64)
+    kn = torch.rand(B, N, generator=g) < frac_known
+    known0[kn] = torch.randint(0, W.CODEBOOK, (int(kn.sum()),), generator=g)
+    cond[:, -(N + 1):-1] = torch.where(known0 == 126336, 126336, known0 + W.TEXT_VOCAB)
+    noise = [(torch.empty(B * N, W.CODEBOOK).exponential_(1, generator=g), torch.rand(B, N, generator=g)) for _ in range(steps)]
+    ids = cond.clone().cuda()
+    trace = []
+    out = m.t2i_generate(input_ids=ids, uncond_input_ids=None, guidance_scale=0.0, timesteps=steps, seq_len=N,
+                         resolution=P - 1, uni_prompting=_UP(), noise=noise, trace=trace)
+    known, temperature = known0.clone(), 1.0
+    sched = denoise.t2i_mask_len_schedule(N, steps)
+    for s, t in enumerate(trace):
+        temperature *= 1.0 - (s + 1) / steps
+        assert t["uncond"] is None
+        r = denoise.t2i_sample_step(t["cond"].cpu(), None, 0.0, known, 126336, sched[s], temperature, *noise[s])
+        assert torch.equal(t["sampled_ids"].cpu(), r["sampled_ids"]) and torch.equal(t["masking"].cpu(), r["masking"]), s
+        # tokens known at entry are never resampled
+        assert torch.equal(r["sampled_ids"][kn], known0[kn])
+        known = r["next_known"]
+    assert torch.equal(out.cpu(), r["sampled_ids"])
+    assert torch.equal(ids[:, :-(N + 1)].cpu(), cond[:, :-(N + 1)])                    # the prompt is untouched
