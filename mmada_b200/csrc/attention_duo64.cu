@@ -11,16 +11,23 @@
 // Here every slot owns two score buffers of 64 fp32 columns (TMEM: 2 slots x 2 x 64 + 2 x 128 for O = 512 columns):
 // while the softmax warps work on sub-tile u in one buffer, the tensor pipe fills the other with the scores of u + 1, so
 // the softmax warps of BOTH slots run back to back (two warps per scheduler, always) and the MMA round trip leaves the
-// critical path.  The price: score MMAs of N = 64 keys run at 48.5 instead of 32 clk per 16 head columns (shared-memory
-// operand bound, profiles/r01_ubench_mma_rate.txt): 2576 clk of tensor work per 128 keys for both slots.
+// critical path.  The price: score MMAs of N = 64 keys run at 48.5 (alone; 59 in this kernel) instead of 32 clk per 16
+// head columns (shared-memory operand bound, profiles/r01_ubench_mma_rate.txt: Q is re-read for every 64 keys) — which
+// is what bounds the kernel now: ~1460 of the 1540 clk per sub-tile of both slots are tensor-pipe time.
 //   * a work item = (batch, head, 256 query rows) = two query tiles ("slots") sharing every K / V tile (128 keys) in
 //     shared memory.  P (bf16) of a sub-tile is written over the first 32 columns of its own score buffer.
-//   * MMA warp, per slot and sub-tile u:  PV(u-2) ; S(u)  — the tensor pipe executes in order, so S(u) may overwrite the
-//     buffer P(u-2) was read from without a barrier.
+//   * one MMA-issuing warp per slot; per sub-tile u:  PV(u-2) ; S(u)  — the tensor pipe executes a thread's MMAs in order,
+//     so S(u) may overwrite the buffer P(u-2) was read from without a barrier.  The pending PVs are drained at the end of
+//     an item (the last one completes O).
 //   * warps 0-3 slot 0, warps 4-7 slot 1: thread per row, 64 scores in registers, speculative exponentials against the
 //     running reference maximum (lazy rescale, growth > 2^8 forces a redo from the registers), row sums in the thread.
-//   * persistent; the sub-tile stream of a slot runs across item boundaries; the softmax threads write their row of O.
-//   warps 0-7 softmax + epilogue (setmaxnreg), warp 8 TMA producer, warps 9 / 10 MMA issuers of slot 0 / 1, warp 11 idle.
+//   * persistent; the softmax threads also write their row of O at the end of an item, through per-warp shared-memory
+//     staging and TMA stores.
+//   * the last item of a sequence may hold one slot only, or a slot with a few rows (L = 1539: 3): the idle slot's issuer
+//     passes the K / V stages on, warps without rows only keep the protocol going, a warp with <= 8 rows shares each row
+//     between four threads — cheaper than a second launch for those rows, which re-reads all of K and V from HBM.
+//   warps 0-7 softmax + epilogue (setmaxnreg 200), warp 8 TMA producer, warps 9 / 10 MMA issuers of slot 0 / 1 (104),
+//   warp 11 idle.
 #include <math.h>
 
 #include <type_traits>
