@@ -426,11 +426,14 @@ static int dispatch_attention(const void* q, const void* k, const void* v, int64
 int launch_attention_duo64(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                            int Lq, int H, float scale, int poly, cudaStream_t stream);
 #ifdef MMADA_EXPERIMENTS
-// EXPERIMENTS builds only (A/B runs): attention_duo.cu = two query tiles in ping-pong with P over
-// its own 128-key score tile (the product kernel before attention_duo64.cu); attention_quad.cu = CTA pairs with two
+// EXPERIMENTS builds only (A/B runs): attention_pair64.cu = attention_duo64.cu on CTA pairs (0.658 ms);
+// attention_duo.cu = two query tiles in ping-pong with P over its own 128-key score tile (the product kernel before
+// attention_duo64.cu); attention_quad.cu = CTA pairs with two
 // 256-row query blocks in flight and P through shared memory; attention_pair.cu = round 1's pair kernel
 int launch_attention_duo(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                          int Lq, int H, float scale, int poly, cudaStream_t stream);
+int launch_attention_pair64(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
+                            int Lq, int H, float scale, int poly, cudaStream_t stream);
 int launch_attention_quad(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
                           int Lq, int H, float scale, int poly, cudaStream_t stream);
 int launch_attention_pair(const void* q, const void* k, const void* v, int64_t ld, void* out, int64_t ldo, int B, int L,
@@ -461,8 +464,9 @@ extern "C" int mmada_attention_bf16(const void* q, const void* k, const void* v,
             // 29.9 ms per step): the split below is kept for A/B runs of the EXPERIMENTS build only.
             auto main_kernel = [&](int Lq) {
 #ifdef MMADA_EXPERIMENTS
-                // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu, 2 attention_quad.cu, 3 attention_duo64.cu (the product's)
+                // MMADA_ATT_KERNEL = 0 round-1 pair kernel, 1 attention_duo.cu, 2 attention_quad.cu, 3 attention_duo64.cu (the product's), 4 attention_pair64.cu
                 static const int which = experiment_env("MMADA_ATT_KERNEL", 3);
+                if (which == 4) return launch_attention_pair64(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 if (which == 1) return launch_attention_duo(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 if (which == 2) return launch_attention_quad(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);
                 if (which == 0) return launch_attention_pair(q, k, v, ld, out, ldo, B, L, Lq, H, scale, attention_poly_env(), s);

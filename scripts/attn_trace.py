@@ -15,6 +15,7 @@ trace = torch.zeros(4 * 64 * 8, dtype=torch.int64, device="cuda")
 lib.mmada_attention_duo_set_trace(ctypes.c_void_p(trace.data_ptr()))
 lib.mmada_attention_quad_set_trace(ctypes.c_void_p(trace.data_ptr()))
 lib.mmada_attention_duo64_set_trace(ctypes.c_void_p(trace.data_ptr()))
+lib.mmada_attention_pair64_set_trace(ctypes.c_void_p(trace.data_ptr()))
 f = lib.mmada_attention_bf16
 f.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
 d = H * hd
