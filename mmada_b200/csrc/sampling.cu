@@ -203,9 +203,18 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
         sum = lane < NW ? s_red[lane] : 0.f;
         sum = warp_add(sum);
         __syncthreads();
-        // ---- argmax of p / q, first index wins ties
+        // ---- argmax of p / q, first index wins ties.  The value that decides is r = fl(fl(e / sum) / q): two IEEE divisions
+        // (reciprocal, Newton steps, range check with an out-of-line slow path — 40 % of the kernel's instructions when every
+        // logit takes them).  Here a logit only takes them when an UPPER bound of its r, three instructions, does not stay
+        // below a value some logit of this warp has already reached (rlb, refreshed across the warp whenever a lane
+        // improves): the expected number of such steps per warp is the harmonic number H_32 = 4 of 32.  Nothing changes in
+        // the result: a skipped logit has r < rlb <= the row's maximum, strictly, so it can neither win nor tie.
+        //   ub >= r:  inv_s >= (1 / sum)(1 + 2^-19) (reciprocal and product rounded up), rcp.approx is within 2^-23 of 1 / q,
+        //   both products are rounded up; r itself carries two roundings of 2^-24.  NaN compares as a candidate.
         float best = -INFINITY, best_p = 0.f;
         int best_i = 0x7fffffff;
+        float rlb = -INFINITY;
+        const float inv_s = __fmul_ru(__frcp_ru(sum), 1.0000019073486328f);
         // the noise is read CH 128-bit loads at a time, only now: the other resident CTAs cover the latency
 #pragma unroll
         for (int i0 = 0; i0 < VEC; i0 += CH) {
@@ -218,9 +227,21 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
                 const float qv[4] = {qq[ii].x, qq[ii].y, qq[ii].z, qq[ii].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float pr = __fdiv_rn(l[i][j], sum);
-                    const float r = __fdiv_rn(pr, qv[j]);
-                    if (r > best) { best = r; best_p = pr; best_i = (i * THREADS + tid) * 4 + j; }
+                    float rq;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(qv[j]));
+                    const float ub = __fmul_ru(__fmul_ru(l[i][j], inv_s), rq);
+                    const bool cand = !(ub < rlb);
+                    if (__any_sync(0xffffffffu, cand)) {
+                        if (cand) {
+                            const float pr = __fdiv_rn(l[i][j], sum);
+                            const float r = __fdiv_rn(pr, qv[j]);
+                            if (r > best) { best = r; best_p = pr; best_i = (i * THREADS + tid) * 4 + j; }
+                        }
+                        float m = best;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        rlb = m;
+                    }
                 }
             }
         }
