@@ -131,6 +131,7 @@ __device__ void remask_row(const float* sel, const float* u, int64_t* known, int
 template <int THREADS, int VEC, int MINB = 1, int CH = VEC>
 __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISampleParams p) {
     __shared__ float s_red[32];
+    __shared__ float s_sum[32];          // (its own array: no barrier is needed between the two reductions' reads and writes)
     __shared__ int s_idx[32];
     __shared__ int s_flag;
     __shared__ int s_cnt;
@@ -187,7 +188,6 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
         __syncthreads();
         mx = s_red[lane < NW ? lane : 0];
         mx = warp_max(mx);
-        __syncthreads();
         // ---- exp and sum
         float sum = 0.f;
 #pragma unroll
@@ -198,11 +198,10 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
                 sum += l[i][j];
             }
         sum = warp_add(sum);
-        if (lane == 0) s_red[warp] = sum;
-        __syncthreads();
-        sum = lane < NW ? s_red[lane] : 0.f;
+        if (lane == 0) s_sum[warp] = sum;
+        __syncthreads();                 // (also orders every thread's read of s_red above before the argmax pass rewrites it)
+        sum = lane < NW ? s_sum[lane] : 0.f;
         sum = warp_add(sum);
-        __syncthreads();
         // ---- argmax of p / q, first index wins ties.  The value that decides is r = fl(fl(e / sum) / q): two IEEE divisions
         // (reciprocal, Newton steps, range check with an out-of-line slow path — 40 % of the kernel's instructions when every
         // logit takes them).  Here a logit only takes them when an UPPER bound of its r, three instructions, does not stay
