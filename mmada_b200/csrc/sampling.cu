@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
     const int b = row / p.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
+    // (the slot of the position's logits is read next to its token, not behind the branch on it: one dependent global
+    // load less in front of the logit loads)
+    const int32_t slot_of_row = p.slot ? __ldg(p.slot + row) : 0;
     const int64_t known = p.known[row];
 
     if (known != p.mask_id && p.raw_out == nullptr) {
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, MINB) t2i_sample_kernel(const T2ISamp
             p.sel_out[row] = FLT_MAX;
         }
     } else {
-        const int64_t lrow = p.slot ? max(p.slot[row], 0) : row;     // (a masked position always has a slot: cap bounds them)
+        const int64_t lrow = p.slot ? max(slot_of_row, 0) : row;     // (a masked position always has a slot: cap bounds them)
         const float4* c4 = reinterpret_cast<const float4*>(p.cond + lrow * p.C);
         const float4* q4 = reinterpret_cast<const float4*>(p.q + (int64_t)row * p.C);
         float l[VEC][4];

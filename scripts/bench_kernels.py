@@ -85,6 +85,14 @@ def main():
             ops.t2i_sample_step(cond, unc, q, u, known, None, 0, tickets, 3.5, 500.0, 0.5, 126336, 126349)
         ms = timeit(run)
         res["t2i_sample_all_masked"] = dict(ms=ms, gbs=3 * B * N * C * 4 / ms / 1e6)
+        # the loop's own form: logits of the still-masked positions only, read through the slot map (all masked here)
+        known0 = torch.full((B, N), 126336, dtype=torch.int64, device="cuda")
+        _, slot = ops.compact_masked_rows(known0, N + 2, 1, N, 2, 126336)
+        def run_c():
+            known = torch.full((B, N), 126336, dtype=torch.int64, device="cuda")
+            ops.t2i_sample_step(cond, unc, q, u, known, None, 0, tickets, 3.5, 500.0, 0.5, 126336, 126349, slot=slot)
+        ms = timeit(run_c)
+        res["t2i_sample_all_masked_compact"] = dict(ms=ms, gbs=3 * B * N * C * 4 / ms / 1e6)
     for k, v in res.items():
         print(k, json.dumps(v))
 
