@@ -6,10 +6,13 @@ Per step the reference materialises fp64 Gumbel noise and an fp64 softmax over t
 logits tensor.  Only still-masked positions of the current block can be transferred (every
 earlier block is complete, every later position is forced to -inf), so
 this implementation computes ln_f + the vocabulary projection + the fp64 sampling chain on the block's
-rows only.  Consequence, stated plainly: with ``temperature > 0`` the uniforms are drawn per
+rows only.  Consequence, stated plainly: with ``temperature > 0`` the uniforms are by default drawn per
 candidate row (in-kernel Philox, or ``noise=`` for parity tests), not as one (B, L, V) draw from the
 global generator, so the random stream differs from the reference's; given the same uniforms the
-decisions are identical.
+decisions are identical.  ``rng="reference"`` makes the reference's own draw instead — one
+``torch.rand((B, L, V), dtype=float64)`` per forward from the device's global generator (generate.py:14:
+``torch.rand_like(logits, dtype=torch.float64)``), of which the block's rows are used — so a seeded generator
+reproduces the reference's stream; it costs the reference's memory for that tensor (B·L·V·8 bytes).
 """
 from __future__ import annotations
 
@@ -38,7 +41,7 @@ def _model_device(model):
 def generate(model, prompt, steps=128, gen_length=128, block_length=128, temperature=0.,
              cfg_scale=0., remasking='low_confidence', mask_id=126336, attention_mask=None, *,
              noise: Optional[Sequence[torch.Tensor]] = None, eot_token: Optional[int] = None, seed: Optional[int] = None,
-             trace: Optional[list] = None, stop_after_steps: Optional[int] = None):
+             trace: Optional[list] = None, stop_after_steps: Optional[int] = None, rng: str = "philox"):
     """Same positional/keyword arguments as the reference.  ``model`` must be an
     ``mmada_b200.LLaDAModelLM`` (it provides ``logits_rows``).  ``attention_mask`` is accepted and has
     no effect, as in the reference (the bias built from it is never applied, Q1).  Precondition: ``prompt`` holds no
@@ -48,6 +51,8 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
     (benchmarking hook: return after that many forwards, sequence length unchanged)."""
     if remasking not in ('low_confidence', 'random'):
         raise NotImplementedError(remasking)
+    if rng not in ("philox", "reference"):
+        raise ValueError(f"rng must be 'philox' or 'reference', not {rng!r}")
     dev = _model_device(model)
     prompt = prompt.to(dev)
     B, Lp = prompt.shape
@@ -90,6 +95,10 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
             u = None
             if noise is not None and temperature != 0:
                 u = noise[k].to(dev).reshape(n, -1).contiguous()
+            elif rng == "reference" and temperature != 0:
+                # the reference's draw: every position of the (B, L, V) logits gets a uniform; the block's rows are read
+                V = logits.shape[-1]
+                u = torch.rand((B, L, V), dtype=torch.float64, device=dev)[:, lo:lo + block_length].reshape(n, V).contiguous()
             x0, conf = ops.text_sample_rows(logits[:n], logits[n:] if cfg else None, cfg_scale, temperature, u,
                                             seed=seed + k)
             override = None
@@ -105,7 +114,7 @@ def generate(model, prompt, steps=128, gen_length=128, block_length=128, tempera
             if trace is not None:
                 trace.append(dict(k=k, block=num_block, step=i, x0=x0.view(B, block_length).clone(),
                                   conf=conf.view(B, block_length).clone(), transfer=tr, x=x.clone(),
-                                  logits=logits.clone(), override=override))     # (a graph replay reuses the buffer)
+                                  logits=logits.clone(), override=override, u=u))     # (a graph replay reuses the buffer)
             k += 1
         if eot_token is not None:
             last = lo + block_length - 1

@@ -173,3 +173,43 @@ def test_generate_random_remasking_matches_oracle_replay(golden):
             xo[j, lo + sel] = x0.view(B, block)[j, sel]
         assert torch.equal(t["x"].cpu(), xo), (nb, i)
     assert torch.equal(x.cpu(), xo) and int((x == 126336).sum()) == 0
+
+
+def test_generate_reference_rng_stream_matches_oracle_replay(golden):
+    """rng='reference': the Gumbel uniforms are the reference's (B, L, V) fp64 draw from the device generator
+    (generate.py:14); with the same seed the same draws replayed on the oracle give the same tokens and states."""
+    import mmada_b200
+    from oracle import denoise, weights as W
+    gd = golden("text_t1")
+    B, Lp, gen, block, steps, wseed, seed = (int(v) for v in gd["meta"])
+    T = float(gd["temperature"])
+    assert T > 0
+    m = _model(W.TINY, wseed)
+    prompt = torch.from_numpy(gd["prompt"])
+    L, V = Lp + gen, W.TINY["vocab_size"]
+    torch.cuda.manual_seed(77)
+    trace = []
+    x = mmada_b200.generate(m, prompt.cuda(), steps=steps, gen_length=gen, block_length=block, temperature=T, rng="reference",
+                            trace=trace)
+    torch.cuda.manual_seed(77)
+    xo = torch.full((B, L), 126336, dtype=torch.long)
+    xo[:, :Lp] = prompt
+    spb = steps // (gen // block)
+    for t in trace:
+        nb, i = t["block"], t["step"]
+        lo = Lp + nb * block
+        u = torch.rand((B, L, V), dtype=torch.float64, device="cuda")[:, lo:lo + block].reshape(B * block, V).cpu()
+        assert torch.equal(t["u"].cpu(), u)
+        if i == 0:
+            ntt = denoise.get_num_transfer_tokens(xo[:, lo:lo + block] == 126336, spb)
+        x0, p = denoise.text_sample_rows(t["logits"].cpu()[:B * block], T, u)
+        assert torch.equal(t["x0"].cpu().reshape(-1), x0)
+        masked = xo[:, lo:lo + block] == 126336
+        conf = torch.where(masked, p.view(B, block), torch.tensor(-np.inf, dtype=torch.float64))
+        for j in range(B):
+            _, sel = torch.topk(conf[j], k=int(ntt[j, i]))
+            xo[j, lo + sel] = x0.view(B, block)[j, sel]
+        assert torch.equal(t["x"].cpu(), xo), (nb, i)
+    assert torch.equal(x.cpu(), xo) and int((x == 126336).sum()) == 0
+    with pytest.raises(ValueError):
+        mmada_b200.generate(m, prompt.cuda(), steps=steps, gen_length=gen, block_length=block, rng="mt19937")
