@@ -286,6 +286,41 @@ class MMadaModelLM(LLaDAModelLM):
                                   attention_mask=attention_mask, eot_token=eot_token, **kwargs)
 
     # ------------------------------------------------------------------------------------------
+    def _loss_rows(self, ids, lab, batch_size_t2i, max_seq_length, segments):
+        """Per-row cross-entropy terms of the training-time forwards: one transformer forward, ``ln_f`` + head + one pass of
+        ``mmada_cross_entropy_rows_f32`` on the token rows a loss reads only — the t2i positions behind the text prefix
+        whose label is not -100 (rows [0, batch_size_t2i)) and the masked positions of every ``segments`` entry (a Python
+        slice of batch rows, in the reference's boolean-mask order).  Returns (nll_t2i, [(nll, mask) per segment])."""
+        dev = self.device
+        B, L = ids.shape
+        masked = ids == self.config.mask_token_id                                             # :246
+        pos = torch.arange(B * L, device=dev, dtype=torch.int64).view(B, L)
+        if batch_size_t2i > 0:
+            t2i_sel = torch.zeros_like(masked)
+            t2i_sel[:batch_size_t2i, max_seq_length + 1:] = lab[:batch_size_t2i, max_seq_length + 1:] != -100
+            rows = [pos[t2i_sel]]
+        else:
+            rows = [pos[:0, 0]]
+        masks = [masked[sl] for sl in segments]
+        rows += [pos[sl][m] for sl, m in zip(segments, masks)]
+        counts = [r.numel() for r in rows]
+        allrows = torch.cat(rows)
+        nll = torch.zeros((0,), dtype=torch.float32, device=dev)
+        if allrows.numel() > 0:
+            lg = self._logits_rows(ids, allrows.to(torch.int32).contiguous())                 # [n_rows, V] fp32 (no graph: the row count changes per batch)
+            nll = ops.cross_entropy_rows(lg, lab.view(-1)[allrows], -100)
+            self.kernel_launches += 1
+            del lg
+        parts = torch.split(nll, counts)
+        return parts[0], list(zip(parts[1:], masks))
+
+    @staticmethod
+    def _t2i_mean(nll_t2i, batch_size_t2i, dev):
+        if batch_size_t2i == 0:
+            return torch.tensor(0.0, device=dev)                                              # :237
+        n = nll_t2i.numel()
+        return nll_t2i.sum() / n if n > 0 else torch.tensor(float("nan"), device=dev)         # mean over the targets
+
     @torch.no_grad()
     def forward_process(self, input_ids, labels, batch_size_t2i=0, batch_size_lm=0, batch_size_mmu=0, max_seq_length=128,
                         p_mask_lm=None, p_mask_mmu=None, answer_lengths=None, t2i_masks=None, answer_lengths_lm=None,
@@ -295,49 +330,62 @@ class MMadaModelLM(LLaDAModelLM):
         lists them), no autograd: this is the evaluation of the losses (validation / logging), the backward pass is out
         of scope.
 
-        What runs underneath: one transformer forward; ``ln_f`` and the output head only on the token rows a loss reads
-        (t2i positions behind the text prefix whose label is not -100, the masked positions of the lm and mmu rows); one
-        pass of ``mmada_cross_entropy_rows_f32`` over those logits.  The reference's ``attention_bias`` from
-        ``t2i_masks`` is never applied by its attention (Q1) and is not built.  ``logits`` is ``None`` unless
-        ``return_logits`` (the reference returns the full (B, L, V) tensor; its training scripts discard it)."""
+        What runs underneath: ``_loss_rows``.  The reference's ``attention_bias`` from ``t2i_masks`` is never applied by
+        its attention (Q1) and is not built.  ``logits`` is ``None`` unless ``return_logits`` (the reference returns the
+        full (B, L, V) tensor; its training scripts discard it)."""
         dev = self.device
-        ids = input_ids.to(dev)
-        lab = labels.to(dev)
+        ids, lab = input_ids.to(dev), labels.to(dev)
         B, L = ids.shape
-        mask_id = self.config.mask_token_id
-        masked = ids == mask_id                                                               # :246
         lo_lm, hi_lm = batch_size_t2i, batch_size_t2i + batch_size_lm
         lo_mmu = (B - batch_size_mmu) if batch_size_mmu > 0 else 0                            # [-0:] is the whole batch (:249)
-        pos = torch.arange(B * L, device=dev, dtype=torch.int64).view(B, L)
-        # loss rows (flattened token-row indices), in the reference's boolean-mask (row-major) order
-        if batch_size_t2i > 0:
-            t2i_sel = torch.zeros_like(masked)
-            t2i_sel[:batch_size_t2i, max_seq_length + 1:] = lab[:batch_size_t2i, max_seq_length + 1:] != -100
-            rows_t2i = pos[t2i_sel]
-        else:
-            rows_t2i = pos[:0, 0]
-        masked_lm = masked[lo_lm:hi_lm]
-        masked_mmu = masked[lo_mmu:]
-        rows_lm = pos[lo_lm:hi_lm][masked_lm]
-        rows_mmu = pos[lo_mmu:][masked_mmu]
-        n_t2i, n_lm = rows_t2i.numel(), rows_lm.numel()
-        rows = torch.cat([rows_t2i, rows_lm, rows_mmu])
-        nll = torch.zeros((0,), dtype=torch.float32, device=dev)
-        if rows.numel() > 0:
-            lg = self._logits_rows(ids, rows.to(torch.int32).contiguous())                    # [n_rows, V] fp32 (no graph: the row count changes per batch)
-            nll = ops.cross_entropy_rows(lg, lab.view(-1)[rows], -100)
-            self.kernel_launches += 1
-            del lg
-        # ---- the reference's reductions, on the per-row losses
-        if batch_size_t2i == 0:
-            loss_t2i = torch.tensor(0.0, device=dev)                                          # :237
-        else:
-            loss_t2i = nll[:n_t2i].sum() / n_t2i if n_t2i > 0 else torch.tensor(float("nan"), device=dev)   # mean over targets
+        nll_t2i, ((nll_lm, masked_lm), (nll_mmu, masked_mmu)) = self._loss_rows(
+            ids, lab, batch_size_t2i, max_seq_length, [slice(lo_lm, hi_lm), slice(lo_mmu, None)])
+        loss_t2i = self._t2i_mean(nll_t2i, batch_size_t2i, dev)
         n_rows_lm = float(max(min(hi_lm, B) - lo_lm, 0))                                      # logits[lm].shape[0]
-        ce_lm = nll[n_t2i:n_t2i + n_lm] / p_mask_lm.to(dev)[masked_lm]                        # :253-256
+        ce_lm = nll_lm / p_mask_lm.to(dev)[masked_lm]                                         # :253-256
         loss_lm = ce_lm.sum() / torch.tensor(n_rows_lm * L, device=dev)                       # :258 (a scalar ...)
         loss_lm = torch.sum(loss_lm / answer_lengths_lm.to(dev)[masked_lm]) / torch.tensor(n_rows_lm, device=dev)   # :262
-        ce_mmu = nll[n_t2i + n_lm:] / p_mask_mmu.to(dev)[masked_mmu]                          # :264-267
+        ce_mmu = nll_mmu / p_mask_mmu.to(dev)[masked_mmu]                                     # :264-267
         loss_mmu = torch.sum(ce_mmu / answer_lengths.to(dev)[masked_mmu]) / float(B - lo_mmu)  # :268
         logits = self.forward(ids).logits if return_logits else None
         return logits, loss_t2i, loss_lm, loss_mmu
+
+    @torch.no_grad()
+    def forward_process_with_r2i(self, input_ids, labels, t2i_masks=None, max_seq_length=128, batch_size_t2i=0,
+                                 batch_size_lm=0, batch_size_mmu=0, batch_size_r2i=0, p_mask_lm=None, p_mask_mmu=None,
+                                 p_mask_r2i=None, answer_lengths=None, answer_lengths_lm=None, answer_lengths_r2i=None,
+                                 return_logits: bool = False):
+        """Forward values of modeling_mmada.py:278-356: like ``forward_process`` with a fourth group of rows (r2i) and
+        explicit [start, end) row ranges for every group (no ``[-n:]`` slices); returns ``(logits, loss_t2i, loss_lm,
+        loss_mmu, loss_r2i)``."""
+        dev = self.device
+        ids, lab = input_ids.to(dev), labels.to(dev)
+        B, L = ids.shape
+        s_lm = batch_size_t2i
+        e_lm = s_lm + batch_size_lm
+        e_mmu = e_lm + batch_size_mmu
+        e_r2i = e_mmu + batch_size_r2i
+        nll_t2i, ((nll_lm, m_lm), (nll_mmu, m_mmu), (nll_r2i, m_r2i)) = self._loss_rows(
+            ids, lab, batch_size_t2i, max_seq_length, [slice(s_lm, e_lm), slice(e_lm, e_mmu), slice(e_mmu, e_r2i)])
+        rows_in = lambda a, b: float(max(min(b, B) - min(a, B), 0))                           # logits[a:b].shape[0]
+        loss_t2i = self._t2i_mean(nll_t2i, batch_size_t2i, dev)
+        n_lm = rows_in(s_lm, e_lm)
+        ce_lm = nll_lm / p_mask_lm.to(dev)[m_lm]
+        loss_lm = ce_lm.sum() / torch.tensor(n_lm * L, device=dev)                            # :335 (a scalar, then :336)
+        loss_lm = torch.sum(loss_lm / answer_lengths_lm.to(dev)[m_lm]) / torch.tensor(n_lm, device=dev)
+        ce_mmu = nll_mmu / p_mask_mmu.to(dev)[m_mmu]
+        loss_mmu = torch.sum(ce_mmu / answer_lengths.to(dev)[m_mmu]) / torch.tensor(rows_in(e_lm, e_mmu), device=dev)
+        ce_r2i = nll_r2i / p_mask_r2i.to(dev)[m_r2i]
+        loss_r2i = torch.sum(ce_r2i / answer_lengths_r2i.to(dev)[m_r2i]) / torch.tensor(rows_in(e_mmu, e_r2i), device=dev)
+        logits = self.forward(ids).logits if return_logits else None
+        return logits, loss_t2i, loss_lm, loss_mmu, loss_r2i
+
+    @torch.no_grad()
+    def forward_t2i(self, input_ids, labels, batch_size_t2i=0, max_seq_length=128, t2i_masks=None):
+        """Forward value of modeling_mmada.py:359-385: the t2i cross-entropy alone (mean over the labelled image positions
+        of the first ``batch_size_t2i`` rows)."""
+        dev = self.device
+        ids, lab = input_ids.to(dev), labels.to(dev)
+        nll_t2i, _ = self._loss_rows(ids, lab, batch_size_t2i, max_seq_length, [])
+        n = nll_t2i.numel()
+        return nll_t2i.sum() / n if n > 0 else torch.tensor(float("nan"), device=dev)         # (no batch_size_t2i == 0 branch there)

@@ -295,6 +295,33 @@ def forward_process_case(name, cfg, B_t2i, B_lm, B_mmu, L, max_seq_length, wseed
           meta=np.array([B_t2i, B_lm, B_mmu, L, max_seq_length, wseed, seed]))
 
 
+def forward_process_r2i_case(name, cfg, B_t2i, B_lm, B_mmu, B_r2i, L, max_seq_length, wseed, seed):
+    """forward_process_with_r2i (modeling_mmada.py:278-356) and forward_t2i (:359-385): the real methods against
+    oracle/training.py.  The batch is training.make_batch's with its last group split into mmu and r2i rows."""
+    print(f"[forward_process_with_r2i / forward_t2i] {name}")
+    sd = W.make_llada_weights(cfg, wseed)
+    model = rb.build_model(cfg, sd)
+    bt = training.make_batch(B_t2i, B_lm, B_mmu + B_r2i, L, max_seq_length, seed, cfg["mask_token_id"])
+    kw = dict(t2i_masks=bt["t2i_masks"], max_seq_length=max_seq_length, batch_size_t2i=B_t2i, batch_size_lm=B_lm,
+              batch_size_mmu=B_mmu, batch_size_r2i=B_r2i, p_mask_lm=bt["p_mask_lm"], p_mask_mmu=bt["p_mask_mmu"][:B_mmu],
+              p_mask_r2i=bt["p_mask_mmu"][B_mmu:], answer_lengths=bt["answer_lengths"][:B_mmu],
+              answer_lengths_lm=bt["answer_lengths_lm"], answer_lengths_r2i=bt["answer_lengths"][B_mmu:])
+    with torch.no_grad():
+        ref = model.forward_process_with_r2i(bt["input_ids"].clone(), bt["labels"].clone(), **kw)
+        ref_t2i = model.forward_t2i(bt["input_ids"].clone(), bt["labels"].clone(), batch_size_t2i=B_t2i,
+                                    max_seq_length=max_seq_length, t2i_masks=bt["t2i_masks"])
+    fn = lambda ids: llada.forward_logits(ids, sd, cfg)
+    mine = training.forward_process_with_r2i(fn, bt["input_ids"].clone(), bt["labels"].clone(),
+                                             mask_token_id=cfg["mask_token_id"], **kw)
+    for a, b, what in zip(ref, mine, ("logits", "loss_t2i", "loss_lm", "loss_mmu", "loss_r2i")):
+        assert torch.equal(a, b), f"restatement != reference (forward_process_with_r2i {what})"
+    mine_t2i = training.forward_t2i(fn, bt["input_ids"].clone(), bt["labels"].clone(), batch_size_t2i=B_t2i,
+                                    max_seq_length=max_seq_length, t2i_masks=bt["t2i_masks"])
+    assert torch.equal(ref_t2i, mine_t2i), "restatement != reference (forward_t2i)"
+    _save(name, loss_t2i=ref[1], loss_lm=ref[2], loss_mmu=ref[3], loss_r2i=ref[4], loss_forward_t2i=ref_t2i,
+          meta=np.array([B_t2i, B_lm, B_mmu, B_r2i, L, max_seq_length, wseed, seed]))
+
+
 def prompting_case():
     """training/prompting_utils.py (the real class, stub tokenizer) against oracle/prompting.py; stores ragged inputs and
     the reference's outputs."""
@@ -388,6 +415,8 @@ def main():
     motion_case()
     prompting_case()
     forward_process_case("forward_process_tiny", W.TINY, B_t2i=2, B_lm=2, B_mmu=2, L=96, max_seq_length=31, wseed=0, seed=41)
+    forward_process_r2i_case("forward_process_r2i_tiny", W.TINY, B_t2i=2, B_lm=1, B_mmu=2, B_r2i=2, L=80, max_seq_length=23,
+                             wseed=0, seed=43)
     logits_case("logits_tiny", W.TINY, 2, 96, 0, 5)
     logits_case("logits_tiny128", W.TINY128, 2, 200, 1, 6)
     t2i_case("t2i_tiny", W.TINY, B=2, P=33, N=64, steps=15, guidance=3.5, wseed=0, pseed=1, gseed=1234)

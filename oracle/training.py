@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows
   * /root/reference/models/modeling_mmada.py:213-276   forward_process: logits + t2i / lm / mmu masked cross-entropy
-    (SURVEY.md section 8 row f4).
+    (SURVEY.md section 8 row f4), :278-356 forward_process_with_r2i, :359-385 forward_t2i.
 Quirks kept literally:
   * the ``attention_bias`` built from ``t2i_masks`` (:228-230) is handed to the model and never applied (Appendix A, Q1),
     so it is not built here;
@@ -48,6 +48,47 @@ def forward_process(logits_fn: Callable[[torch.Tensor], torch.Tensor], input_ids
                                reduction="none") / p_mask_mmu[masked_mmu]                      # :264-267
     loss_mmu = torch.sum(loss_mmu / answer_lengths[masked_mmu]) / logits[-batch_size_mmu:].shape[0]   # :268
     return logits, loss_t2i, loss_lm, loss_mmu
+
+
+def forward_process_with_r2i(logits_fn, input_ids, labels, t2i_masks=None, max_seq_length=128, batch_size_t2i=0,
+                             batch_size_lm=0, batch_size_mmu=0, batch_size_r2i=0, p_mask_lm=None, p_mask_mmu=None,
+                             p_mask_r2i=None, answer_lengths=None, answer_lengths_lm=None, answer_lengths_r2i=None,
+                             mask_token_id: int = 126336):
+    """/root/reference/models/modeling_mmada.py:278-356: forward_process with a fourth group (r2i) and explicit row ranges."""
+    logits = logits_fn(input_ids)
+    V = logits.shape[-1]
+    if batch_size_t2i == 0:
+        loss_t2i = torch.tensor(0.0, device=input_ids.device)
+    else:
+        loss_t2i = F.cross_entropy(logits[:batch_size_t2i, max_seq_length + 1:].contiguous().view(-1, V),
+                                   labels[:batch_size_t2i, max_seq_length + 1:].contiguous().view(-1), ignore_index=-100)
+    s_lm = batch_size_t2i
+    e_lm = s_lm + batch_size_lm
+    e_mmu = e_lm + batch_size_mmu
+    e_r2i = e_mmu + batch_size_r2i
+    masked = input_ids == mask_token_id
+
+    def group(a, b, p_mask):
+        m = masked[a:b]
+        return F.cross_entropy(logits[a:b][m].contiguous().view(-1, V), labels[a:b][m].contiguous().view(-1),
+                               ignore_index=-100, reduction="none") / p_mask[m], m
+
+    loss_lm, m_lm = group(s_lm, e_lm, p_mask_lm)
+    loss_lm = loss_lm.sum() / (logits[s_lm:e_lm].shape[0] * logits[s_lm:e_lm].shape[1])
+    loss_lm = torch.sum(loss_lm / answer_lengths_lm[m_lm]) / logits[s_lm:e_lm].shape[0]
+    loss_mmu, m_mmu = group(e_lm, e_mmu, p_mask_mmu)
+    loss_mmu = torch.sum(loss_mmu / answer_lengths[m_mmu]) / logits[e_lm:e_mmu].shape[0]
+    loss_r2i, m_r2i = group(e_mmu, e_r2i, p_mask_r2i)
+    loss_r2i = torch.sum(loss_r2i / answer_lengths_r2i[m_r2i]) / logits[e_mmu:e_r2i].shape[0]
+    return logits, loss_t2i, loss_lm, loss_mmu, loss_r2i
+
+
+def forward_t2i(logits_fn, input_ids, labels, batch_size_t2i=0, max_seq_length=128, t2i_masks=None):
+    """/root/reference/models/modeling_mmada.py:359-385."""
+    logits = logits_fn(input_ids)
+    V = logits.shape[-1]
+    return F.cross_entropy(logits[:batch_size_t2i, max_seq_length + 1:].contiguous().view(-1, V),
+                           labels[:batch_size_t2i, max_seq_length + 1:].contiguous().view(-1), ignore_index=-100)
 
 
 def make_batch(B_t2i: int, B_lm: int, B_mmu: int, L: int, max_seq_length: int, seed: int, mask_token_id: int = 126336,

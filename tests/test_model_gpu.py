@@ -292,3 +292,27 @@ def test_t2i_generate_without_cfg_and_with_known_tokens(B, frac_known):
         known = r["next_known"]
     assert torch.equal(out.cpu(), r["sampled_ids"])
     assert torch.equal(ids[:, :-(N + 1)].cpu(), cond[:, :-(N + 1)])                    # the prompt is untouched
+
+
+def test_forward_process_with_r2i_and_forward_t2i_match_reference_golden(golden):
+    """forward_process_with_r2i (modeling_mmada.py:278-356) and forward_t2i (:359-385), forward values: against the CPU oracle
+    on the CUDA path's own logits (1e-5) and against the REAL reference's fp32 losses (2e-2)."""
+    from mmada_b200 import MMadaConfig, MMadaModelLM
+    from oracle import training, weights as W
+    gd = golden("forward_process_r2i_tiny")
+    B_t2i, B_lm, B_mmu, B_r2i, L, msl, wseed, seed = (int(v) for v in gd["meta"])
+    m = MMadaModelLM(MMadaConfig.from_dict(W.TINY)).load_state_dict(W.make_llada_weights(W.TINY, wseed))
+    bt = training.make_batch(B_t2i, B_lm, B_mmu + B_r2i, L, msl, seed, W.TINY["mask_token_id"])
+    kw = dict(t2i_masks=bt["t2i_masks"], max_seq_length=msl, batch_size_t2i=B_t2i, batch_size_lm=B_lm, batch_size_mmu=B_mmu,
+              batch_size_r2i=B_r2i, p_mask_lm=bt["p_mask_lm"], p_mask_mmu=bt["p_mask_mmu"][:B_mmu],
+              p_mask_r2i=bt["p_mask_mmu"][B_mmu:], answer_lengths=bt["answer_lengths"][:B_mmu],
+              answer_lengths_lm=bt["answer_lengths_lm"], answer_lengths_r2i=bt["answer_lengths"][B_mmu:])
+    ids, lab = bt["input_ids"].cuda(), bt["labels"].cuda()
+    out = m.forward_process_with_r2i(ids, lab, return_logits=True, **kw)
+    full = out[0].cpu()
+    orc = training.forward_process_with_r2i(lambda x: full, bt["input_ids"], bt["labels"], mask_token_id=W.TINY["mask_token_id"], **kw)
+    for mine, o, name in zip(out[1:], orc[1:], ("loss_t2i", "loss_lm", "loss_mmu", "loss_r2i")):
+        a, b, c = float(mine), float(o), float(gd[name])
+        assert abs(a - b) <= 1e-5 * abs(b) and abs(a - c) <= 2e-2 * abs(c), (name, a, b, c)
+    t2i = float(m.forward_t2i(ids, lab, batch_size_t2i=B_t2i, max_seq_length=msl, t2i_masks=bt["t2i_masks"]))
+    assert t2i == float(out[1]) and abs(t2i - float(gd["loss_forward_t2i"])) <= 2e-2 * abs(float(gd["loss_forward_t2i"]))

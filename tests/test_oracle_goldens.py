@@ -144,3 +144,23 @@ def test_forward_process_oracle_reproduces_reference_losses(golden):
         mask_token_id=W.TINY["mask_token_id"])
     assert np.array_equal(lg[:, ::5, ::997].numpy(), gd["logits_sub"])
     assert float(l_t2i) == float(gd["loss_t2i"]) and float(l_lm) == float(gd["loss_lm"]) and float(l_mmu) == float(gd["loss_mmu"])
+
+
+def test_forward_process_r2i_oracle_reproduces_reference_losses(golden):
+    """oracle/training.py: forward_process_with_r2i and forward_t2i against the REAL methods' stored losses, bit for bit."""
+    from oracle import llada, training, weights as W
+    gd = golden("forward_process_r2i_tiny")
+    B_t2i, B_lm, B_mmu, B_r2i, L, msl, wseed, seed = (int(v) for v in gd["meta"])
+    sd = W.make_llada_weights(W.TINY, wseed)
+    bt = training.make_batch(B_t2i, B_lm, B_mmu + B_r2i, L, msl, seed, W.TINY["mask_token_id"])
+    fn = lambda ids: llada.forward_logits(ids, sd, W.TINY)
+    out = training.forward_process_with_r2i(
+        fn, bt["input_ids"], bt["labels"], t2i_masks=bt["t2i_masks"], max_seq_length=msl, batch_size_t2i=B_t2i,
+        batch_size_lm=B_lm, batch_size_mmu=B_mmu, batch_size_r2i=B_r2i, p_mask_lm=bt["p_mask_lm"],
+        p_mask_mmu=bt["p_mask_mmu"][:B_mmu], p_mask_r2i=bt["p_mask_mmu"][B_mmu:], answer_lengths=bt["answer_lengths"][:B_mmu],
+        answer_lengths_lm=bt["answer_lengths_lm"], answer_lengths_r2i=bt["answer_lengths"][B_mmu:],
+        mask_token_id=W.TINY["mask_token_id"])
+    for v, name in zip(out[1:], ("loss_t2i", "loss_lm", "loss_mmu", "loss_r2i")):
+        assert float(v) == float(gd[name]), name
+    t2i = training.forward_t2i(fn, bt["input_ids"], bt["labels"], batch_size_t2i=B_t2i, max_seq_length=msl, t2i_masks=bt["t2i_masks"])
+    assert float(t2i) == float(gd["loss_forward_t2i"])
